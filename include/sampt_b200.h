@@ -1,0 +1,74 @@
+/* libsampt_b200.so — C ABI of the B200-native SAM-PT hot path.
+ *
+ * The reference (SysCV/sam-pt) has NO FFI: its seam is Python classes named in Hydra YAML.  This
+ * library sits BEHIND drop-in replacements of those classes (sam-pt_b200/sam_pt, sam-pt_b200/segment_anything[_hq])
+ * and is bound with ctypes (sam-pt_b200/sampt_b200/native.py).  Each entry point below cites the reference code it
+ * replaces.  Conventions:
+ *   - extern "C", plain pointers and sizes, no torch types; every function returns int (0 = ok, <0 = error) and
+ *     sampt_last_error() returns a thread-local message; Python surfaces non-zero codes as RuntimeError.
+ *   - all tensor arguments are caller-owned DEVICE pointers unless the name ends in _host; layouts are stated per call.
+ *   - every call takes a cudaStream_t (as void*) and is stream-ordered; only sampt_pips_track synchronises
+ *     the stream (once per processed window, to read back N ints of linking state).
+ *   - a ctx belongs to one device and is not thread-safe; distinct ctxs are independent.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef SAMPT_B200_H
+#define SAMPT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sampt_ctx sampt_ctx;
+
+/* dtype codes for sampt_set_tensor */
+#define SAMPT_F32 0
+#define SAMPT_F16 1
+#define SAMPT_U8 2
+#define SAMPT_I32 3
+#define SAMPT_BF16 4
+
+/* ---- context / registry -------------------------------------------------------------------------------------- */
+const char* sampt_last_error(void);
+int sampt_version(void);
+int sampt_ctx_create(int device, sampt_ctx** out);
+int sampt_ctx_destroy(sampt_ctx* ctx);
+/* caller-owned scratch slab that pipelines bump-allocate from (no cudaMalloc inside the library) */
+int sampt_ctx_set_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes);
+/* register a caller-owned device tensor under a name (weights in kernel-native layout; replaces the
+ * load_state_dict contract of sam_pt/modeling/sam.py:18-31 and sam_pt/point_tracker/utils/saverloader.py:30-73) */
+int sampt_set_tensor(sampt_ctx* ctx, const char* name, void* dev_ptr, int dtype, int ndim, const int64_t* dims);
+/* number of kernels launched through this ctx since creation (bench.py reports the delta as gpu_launches) */
+long long sampt_launch_count(sampt_ctx* ctx);
+
+/* ---- PIPS point tracker -------------------------------------------------------------------------------------- */
+/* BasicEncoder over uint8 frames (T,3,H,W) -> fmaps (T,H/4,W/4,128) fp32 channels-last.
+ * Replaces Pips.forward's `rgbs = 2*(rgbs/255)-1; fmaps = self.fnet(rgbs_)` (sam_pt/point_tracker/pips/pips.py:446-455,
+ * BasicEncoder.forward :254-287), computed once per frame instead of once per window. */
+int sampt_pips_fnet(sampt_ctx* ctx, const uint8_t* frames_u8, int T, int H, int W, int stride, float* fmaps, void* stream);
+/* CorrBlock.__init__ (pips.py:345-362): avg_pool2d pyramid levels 1..3, channels-last. */
+int sampt_pips_pyramid(sampt_ctx* ctx, const float* fmaps, int T, int H4, int W4, float* l1, float* l2, float* l3,
+                       void* stream);
+/* PipsPointTracker._forward (sam_pt/point_tracker/pips/tracker.py:42-153) incl. Pips.forward's iteration loop
+ * (pips.py:507-568).  query_points (N,3)=(t,x,y) device fp32; traj (T,N,2), vis (T,N) sigmoid visibilities (NOT yet
+ * thresholded at 0.5).  flip != 0 runs the time-reversed pass (tracker.py:161-166); outputs are then in flipped time.
+ * max_windows > 0 stops after that many processed windows (1 == a single Pips.forward call; 0 = whole clip). */
+int sampt_pips_track(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3, int T, int H4,
+                     int W4, const float* query_points, int N, int S, int stride, float thr0, int iters, int flip,
+                     int max_windows, float* traj, float* vis, void* stream);
+/* CorrBlock.corr + CorrBlock.sample (pips.py:364-407) fused, for S window slots: ffeats (N,S,128), coords (N,S,2) in
+ * level-0 feature pixels, pyramid levels (S,H_l,W_l,128) -> fcorr (N,S,196). */
+int sampt_pips_corr_lookup(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3, int S,
+                           int H4, int W4, const float* ffeats, const float* coords, int N, float* fcorr, void* stream);
+
+/* ---- generic fp32 linear (unit tests; torch.nn.functional.linear semantics) ----------------------------------- */
+/* Y[M,N] = act(X[M,K] W[N,K]^T + bias) (+ residual); act 0 none / 1 GELU(erf) / 2 ReLU; K,ldx,ldw multiples of 4 */
+int sampt_linear_f32(sampt_ctx* ctx, const float* X, int ldx, const float* W, int ldw, const float* bias,
+                     const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAMPT_B200_H */

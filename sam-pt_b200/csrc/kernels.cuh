@@ -1,0 +1,50 @@
+// Internal launcher declarations shared by the pipelines (not part of the C ABI; see include/sampt_b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace sampt {
+
+// ---- fp32 GEMM (sgemm.cu):  Y = act(X W^T + bias) (+ residual);  act: 0 none, 1 GELU(erf), 2 ReLU
+int sgemm_nt(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
+             const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act);
+
+// ---- PIPS (pips_kernels.cu)
+struct PipsWin {
+  int N, S, stride, frame, T;
+  int fidx[8];             // real frame index feeding window slot s (handles tail padding and the flipped pass)
+  const float* pyr[4];     // pyramid level base pointers, each (T, H_l, W_l, 128) channels-last
+  int H[4], W[4];
+  float* coords;           // (N, S, 2) feature-map pixels
+  float* ffeats;           // (N, S, 128)
+  float* feat_init;        // (N, 128)
+  float* traj;             // (T, N, 2) image pixels (pass-local time order)
+  float* vis;              // (T, N)
+  int* cur;                // (N) current_point_frames
+  const uint8_t* active;   // (N) 1 = point takes part in this window
+  int sample_feat;         // 1: feat_init <- bilinear_sample2d(fmaps[slot 0]) (init pass), 0: use stored feat_init
+};
+
+int conv_nhwc_f32(Ctx* c, cudaStream_t st, const float* in, const float* w, const float* bias, float* out, int Nimg,
+                  int H, int W, int Cin, int Cout, int R, int S, int stride, int pad);
+int inorm_stats(Ctx* c, cudaStream_t st, const float* x, float* stats, double* part, int Nimg, int HW, int C);
+int inorm_apply(Ctx* c, cudaStream_t st, const float* x, const float* stats, const float* res, const float* res_stats,
+                float* y, int Nimg, int HW, int C, int relu_before_add, int relu_after);
+int resize_ac_concat(Ctx* c, cudaStream_t st, const float* in, float* out, int Nimg, int Hi, int Wi, int C, int Ho, int Wo,
+                     int Ctot, int coff);
+int avgpool2_nhwc(Ctx* c, cudaStream_t st, const float* in, float* out, int Nimg, int Hi, int Wi, int C);
+int pips_window_init(Ctx* c, cudaStream_t st, const PipsWin& w);
+int pips_corr(Ctx* c, cudaStream_t st, const PipsWin& w, float* xin, int ldx);
+int pips_corr_only(Ctx* c, cudaStream_t st, const PipsWin& w, float* fcorr);
+int mixer_token(Ctx* c, cudaStream_t st, float* x, float* xln, const uint8_t* active, int N, const float* ln_w,
+                const float* ln_b, const float* w1, const float* b1, const float* w2, const float* b2, const float* ln2_w,
+                const float* ln2_b, int do_token_mix);
+int mixer_mean(Ctx* c, cudaStream_t st, const float* xln, float* xm, int N, int S, int D);
+int pips_update(Ctx* c, cudaStream_t st, const PipsWin& w, const float* delta, const float* gn_w, const float* gn_b,
+                const float* up_w, const float* up_b);
+int pips_link(Ctx* c, cudaStream_t st, const PipsWin& w, const float* vis_w, const float* vis_b, float thr0, int T,
+              int n_missing);
+
+__global__ void conv7x7s2_u8_kernel(const uint8_t* frames, const float* w, const float* bias, float* out, int H, int W,
+                                    int Ho, int Wo);
+
+}  // namespace sampt

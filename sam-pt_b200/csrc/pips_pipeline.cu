@@ -1,0 +1,326 @@
+// Host-side orchestration of the PIPS path (C++; one stream, no Python in the loop).
+//   sampt_pips_fnet      : BasicEncoder over frames, computed ONCE per frame (InstanceNorm has no running stats so
+//                          per-frame features are window-independent)         pips.py:254-287
+//   sampt_pips_pyramid   : avg-pool pyramid                                                    pips.py:355-361
+//   sampt_pips_track     : sliding-window chain with trajectory linking                        pips/tracker.py:42-153
+#include "common.cuh"
+#include "kernels.cuh"
+#include "../../include/sampt_b200.h"
+
+namespace sampt {
+
+struct Act {  // channels-last activation
+  float* p; int n, h, w, c;
+  size_t numel() const { return (size_t)n * h * w * c; }
+};
+
+static int alloc_act(Ctx* c, Act* a, int n, int h, int w, int ch, const char* what) {
+  a->n = n; a->h = h; a->w = w; a->c = ch;
+  return ws_get(c, &a->p, a->numel(), what);
+}
+
+struct FnetScratch { float* stats_a; float* stats_b; double* part; };
+
+static int conv_by_name(Ctx* c, cudaStream_t st, const std::string& name, const Act& in, Act* out, int R, int stride, int pad) {
+  const float *w, *b;
+  SAMPT_TRY(get_f32(c, "pips." + name + ".weight_rsck", &w));
+  SAMPT_TRY(get_f32(c, "pips." + name + ".bias", &b));
+  return conv_nhwc_f32(c, st, in.p, w, b, out->p, in.n, in.h, in.w, in.c, out->c, R, R, stride, pad);
+}
+
+// ResidualBlock (pips.py:139-188): y = relu(IN(conv1 x)); y = relu(IN(conv2 y)); x' = IN(conv1x1 x) if stride>1; relu(x'+y)
+// s1/s2/s3 are scratch buffers at least as large as the block's output.
+static int res_block(Ctx* c, cudaStream_t st, const std::string& p, const Act& x, Act* out, int planes, int stride,
+                     float* s1, float* s2, float* s3, FnetScratch& s) {
+  const int ho = (x.h + 2 - 3) / stride + 1, wo = (x.w + 2 - 3) / stride + 1;
+  Act y1{s1, x.n, ho, wo, planes}, y2{s2, x.n, ho, wo, planes}, ds{s3, x.n, ho, wo, planes};
+  SAMPT_TRY(conv_by_name(c, st, p + "conv1", x, &y1, 3, stride, 1));
+  SAMPT_TRY(inorm_stats(c, st, y1.p, s.stats_a, s.part, x.n, ho * wo, planes));
+  SAMPT_TRY(inorm_apply(c, st, y1.p, s.stats_a, nullptr, nullptr, y1.p, x.n, ho * wo, planes, 1, 0));
+  SAMPT_TRY(conv_by_name(c, st, p + "conv2", y1, &y2, 3, 1, 1));
+  SAMPT_TRY(inorm_stats(c, st, y2.p, s.stats_a, s.part, x.n, ho * wo, planes));
+  out->n = x.n; out->h = ho; out->w = wo; out->c = planes;
+  if (stride == 1) {
+    SAMPT_TRY(inorm_apply(c, st, y2.p, s.stats_a, x.p, nullptr, out->p, x.n, ho * wo, planes, 1, 1));
+  } else {
+    SAMPT_TRY(conv_by_name(c, st, p + "downsample.0", x, &ds, 1, stride, 0));
+    SAMPT_TRY(inorm_stats(c, st, ds.p, s.stats_b, s.part, x.n, ho * wo, planes));
+    SAMPT_TRY(inorm_apply(c, st, y2.p, s.stats_a, ds.p, s.stats_b, out->p, x.n, ho * wo, planes, 1, 1));
+  }
+  return 0;
+}
+
+static int fnet_chunk(Ctx* c, cudaStream_t st, const uint8_t* frames, int n, int H, int W, int stride, float* fmaps_out) {
+  const int H2 = (H + 6 - 7) / 2 + 1, W2 = (W + 6 - 7) / 2 + 1;
+  const int Ho = H / stride, Wo = W / stride;
+  size_t big = (size_t)n * H2 * W2 * 64;  // largest activation (also >= later stages: 96ch at /4 res etc.)
+  size_t cat_elems = (size_t)n * Ho * Wo * 416;
+  float *bufA, *bufB, *bufC, *bufD, *bufE;
+  SAMPT_TRY(ws_get(c, &bufA, big, "fnet bufA"));
+  SAMPT_TRY(ws_get(c, &bufB, big, "fnet bufB"));
+  SAMPT_TRY(ws_get(c, &bufC, big, "fnet bufC"));
+  SAMPT_TRY(ws_get(c, &bufD, big, "fnet bufD"));
+  SAMPT_TRY(ws_get(c, &bufE, big, "fnet bufE"));
+  float* cat;
+  SAMPT_TRY(ws_get(c, &cat, cat_elems, "fnet concat"));
+  FnetScratch s;
+  SAMPT_TRY(ws_get(c, &s.stats_a, (size_t)n * 256 * 2, "stats_a"));
+  SAMPT_TRY(ws_get(c, &s.stats_b, (size_t)n * 256 * 2, "stats_b"));
+  int nchunks = cdiv((long long)H2 * W2, 512);
+  SAMPT_TRY(ws_get(c, &s.part, (size_t)n * nchunks * 256 * 2, "inorm partials"));
+
+  const float *w1, *b1;
+  SAMPT_TRY(get_f32(c, "pips.fnet.conv1.weight_rsck", &w1));
+  SAMPT_TRY(get_f32(c, "pips.fnet.conv1.bias", &b1));
+  Act x{bufA, n, H2, W2, 64};
+  dim3 g(cdiv((long long)H2 * W2, 64), n);
+  conv7x7s2_u8_kernel<<<g, 256, 0, st>>>(frames, w1, b1, x.p, H, W, H2, W2);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  SAMPT_TRY(inorm_stats(c, st, x.p, s.stats_a, s.part, n, H2 * W2, 64));
+  SAMPT_TRY(inorm_apply(c, st, x.p, s.stats_a, nullptr, nullptr, x.p, n, H2 * W2, 64, 1, 0));
+
+  float *t1 = bufC, *t2 = bufD, *t3 = bufE;
+  // layer1 (64, stride 1)
+  Act a0{bufB, 0, 0, 0, 0}, a{bufA, 0, 0, 0, 0};
+  SAMPT_TRY(res_block(c, st, "fnet.layer1.0.", x, &a0, 64, 1, t1, t2, t3, s));
+  SAMPT_TRY(res_block(c, st, "fnet.layer1.1.", a0, &a, 64, 1, t1, t2, t3, s));  // a lives in bufA
+  SAMPT_TRY(resize_ac_concat(c, st, a.p, cat, n, a.h, a.w, 64, Ho, Wo, 416, 0));
+  // layer2 (96, stride 2)
+  Act b0{bufB, 0, 0, 0, 0}, b{bufA, 0, 0, 0, 0};
+  SAMPT_TRY(res_block(c, st, "fnet.layer2.0.", a, &b0, 96, 2, t1, t2, t3, s));
+  SAMPT_TRY(res_block(c, st, "fnet.layer2.1.", b0, &b, 96, 1, t1, t2, t3, s));
+  SAMPT_TRY(resize_ac_concat(c, st, b.p, cat, n, b.h, b.w, 96, Ho, Wo, 416, 64));
+  // layer3 (128, stride 2)
+  Act c0{bufB, 0, 0, 0, 0}, cc{bufA, 0, 0, 0, 0};
+  SAMPT_TRY(res_block(c, st, "fnet.layer3.0.", b, &c0, 128, 2, t1, t2, t3, s));
+  SAMPT_TRY(res_block(c, st, "fnet.layer3.1.", c0, &cc, 128, 1, t1, t2, t3, s));
+  SAMPT_TRY(resize_ac_concat(c, st, cc.p, cat, n, cc.h, cc.w, 128, Ho, Wo, 416, 160));
+  // layer4 (128, stride 2)
+  Act d0{bufB, 0, 0, 0, 0}, d{bufA, 0, 0, 0, 0};
+  SAMPT_TRY(res_block(c, st, "fnet.layer4.0.", cc, &d0, 128, 2, t1, t2, t3, s));
+  SAMPT_TRY(res_block(c, st, "fnet.layer4.1.", d0, &d, 128, 1, t1, t2, t3, s));
+  SAMPT_TRY(resize_ac_concat(c, st, d.p, cat, n, d.h, d.w, 128, Ho, Wo, 416, 288));
+  // conv2 3x3 416->256, IN, ReLU, conv3 1x1 256->128 (pips.py:279-282)
+  Act catA{cat, n, Ho, Wo, 416};
+  Act y{bufB, n, Ho, Wo, 256};
+  SAMPT_TRY(conv_by_name(c, st, "fnet.conv2", catA, &y, 3, 1, 1));
+  SAMPT_TRY(inorm_stats(c, st, y.p, s.stats_a, s.part, n, Ho * Wo, 256));
+  SAMPT_TRY(inorm_apply(c, st, y.p, s.stats_a, nullptr, nullptr, y.p, n, Ho * Wo, 256, 1, 0));
+  Act out{fmaps_out, n, Ho, Wo, 128};
+  SAMPT_TRY(conv_by_name(c, st, "fnet.conv3", y, &out, 1, 1, 0));
+  return 0;
+}
+
+}  // namespace sampt
+
+using namespace sampt;
+
+extern "C" int sampt_pips_fnet(sampt_ctx* ctx, const uint8_t* frames_u8, int T, int H, int W, int stride, float* fmaps,
+                               void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SAMPT_CHECK(stride == 4, "sampt_pips_fnet: only stride 4 (configs/model/point_tracker/pips.yaml:3) is built, got %d", stride);
+  const int Ho = H / stride, Wo = W / stride;
+  // chunk frames so the fp32 half-res activations fit the workspace (6 buffers of n*H2*W2*64 floats + concat)
+  const int H2 = (H + 6 - 7) / 2 + 1, W2 = (W + 6 - 7) / 2 + 1;
+  size_t per_frame = ((size_t)H2 * W2 * 64 * 5 + (size_t)Ho * Wo * 416) * sizeof(float) + (1 << 20);
+  int chunk = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, (c->ws_bytes - (8u << 20)) / per_frame));
+  SAMPT_CHECK(c->ws_bytes > per_frame + (8u << 20), "workspace too small for one frame of fnet (%zu needed)", per_frame + (8u << 20));
+  if (chunk > 16) chunk = 16;
+  for (int t0 = 0; t0 < T; t0 += chunk) {
+    int n = std::min(chunk, T - t0);
+    c->ws_reset();
+    SAMPT_TRY(fnet_chunk(c, st, frames_u8 + (size_t)t0 * 3 * H * W, n, H, W, stride, fmaps + (size_t)t0 * Ho * Wo * 128));
+  }
+  return 0;
+}
+
+extern "C" int sampt_pips_pyramid(sampt_ctx* ctx, const float* fmaps, int T, int H4, int W4, float* l1, float* l2,
+                                  float* l3, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SAMPT_TRY(avgpool2_nhwc(c, st, fmaps, l1, T, H4, W4, 128));
+  SAMPT_TRY(avgpool2_nhwc(c, st, l1, l2, T, H4 / 2, W4 / 2, 128));
+  SAMPT_TRY(avgpool2_nhwc(c, st, l2, l3, T, H4 / 4, W4 / 4, 128));
+  return 0;
+}
+
+namespace sampt {
+
+__global__ void set_active_kernel(const int* __restrict__ v, int f, uint8_t* __restrict__ active, int N) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) active[n] = (v[n] == f) ? 1 : 0;
+}
+__global__ void track_state_init_kernel(const float* __restrict__ q, float* traj, float* vis, int* start, int* cur, int T, int N,
+                                        int flip) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int t = (int)q[n * 3 + 0];  // .long() truncation (pips/tracker.py:57)
+  if (flip) t = T - 1 - t;     // query_points_flipped (pips/tracker.py:162-164)
+  start[n] = t; cur[n] = t;
+  vis[(size_t)t * N + n] = 1.0f;
+  traj[((size_t)t * N + n) * 2 + 0] = q[n * 3 + 1];
+  traj[((size_t)t * N + n) * 2 + 1] = q[n * 3 + 2];
+}
+
+struct MixerW {
+  const float *w0, *b0;
+  const float *ln0_w[12], *ln0_b[12], *tw1[12], *tb1[12], *tw2[12], *tb2[12];
+  const float *ln1_w[12], *ln1_b[12], *cw1[12], *cb1[12], *cw2[12], *cb2[12];
+  const float *lnf_w, *lnf_b, *w15, *b15;
+  const float *gn_w, *gn_b, *up_w, *up_b, *vis_w, *vis_b;
+};
+
+static int load_mixer(Ctx* c, MixerW* m) {
+  const std::string p = "pips.delta_block.to_delta.";
+  SAMPT_TRY(get_f32(c, p + "0.weight_kpad", &m->w0));
+  SAMPT_TRY(get_f32(c, p + "0.bias", &m->b0));
+  for (int l = 0; l < 12; ++l) {
+    std::string q = p + std::to_string(l + 1);
+    SAMPT_TRY(get_f32(c, q + ".0.norm.weight", &m->ln0_w[l]));
+    SAMPT_TRY(get_f32(c, q + ".0.norm.bias", &m->ln0_b[l]));
+    SAMPT_TRY(get_f32(c, q + ".0.fn.0.weight", &m->tw1[l]));
+    SAMPT_TRY(get_f32(c, q + ".0.fn.0.bias", &m->tb1[l]));
+    SAMPT_TRY(get_f32(c, q + ".0.fn.3.weight", &m->tw2[l]));
+    SAMPT_TRY(get_f32(c, q + ".0.fn.3.bias", &m->tb2[l]));
+    SAMPT_TRY(get_f32(c, q + ".1.norm.weight", &m->ln1_w[l]));
+    SAMPT_TRY(get_f32(c, q + ".1.norm.bias", &m->ln1_b[l]));
+    SAMPT_TRY(get_f32(c, q + ".1.fn.0.weight", &m->cw1[l]));
+    SAMPT_TRY(get_f32(c, q + ".1.fn.0.bias", &m->cb1[l]));
+    SAMPT_TRY(get_f32(c, q + ".1.fn.3.weight", &m->cw2[l]));
+    SAMPT_TRY(get_f32(c, q + ".1.fn.3.bias", &m->cb2[l]));
+  }
+  SAMPT_TRY(get_f32(c, p + "13.weight", &m->lnf_w));
+  SAMPT_TRY(get_f32(c, p + "13.bias", &m->lnf_b));
+  SAMPT_TRY(get_f32(c, p + "15.weight", &m->w15));
+  SAMPT_TRY(get_f32(c, p + "15.bias", &m->b15));
+  SAMPT_TRY(get_f32(c, "pips.norm.weight", &m->gn_w));
+  SAMPT_TRY(get_f32(c, "pips.norm.bias", &m->gn_b));
+  SAMPT_TRY(get_f32(c, "pips.ffeat_updater.0.weight", &m->up_w));
+  SAMPT_TRY(get_f32(c, "pips.ffeat_updater.0.bias", &m->up_b));
+  SAMPT_TRY(get_f32(c, "pips.vis_predictor.0.weight", &m->vis_w));
+  SAMPT_TRY(get_f32(c, "pips.vis_predictor.0.bias", &m->vis_b));
+  return 0;
+}
+
+struct IterBufs { float *xin, *x, *xln, *h, *xm, *delta; };
+
+// one refinement iteration of Pips.forward (pips.py:507-546)
+static int pips_iteration(Ctx* c, cudaStream_t st, const PipsWin& w, const MixerW& m, const IterBufs& b) {
+  const int M = w.N * w.S;
+  SAMPT_TRY(pips_corr(c, st, w, b.xin, 520));
+  SAMPT_TRY(sgemm_nt(c, st, b.xin, 520, m.w0, 520, m.b0, nullptr, 0, b.x, 512, M, 512, 520, 0));
+  for (int l = 0; l < 12; ++l) {
+    SAMPT_TRY(mixer_token(c, st, b.x, b.xln, w.active, w.N, m.ln0_w[l], m.ln0_b[l], m.tw1[l], m.tb1[l], m.tw2[l], m.tb2[l],
+                          m.ln1_w[l], m.ln1_b[l], 1));
+    SAMPT_TRY(sgemm_nt(c, st, b.xln, 512, m.cw1[l], 512, m.cb1[l], nullptr, 0, b.h, 2048, M, 2048, 512, 1));
+    SAMPT_TRY(sgemm_nt(c, st, b.h, 2048, m.cw2[l], 2048, m.cb2[l], b.x, 512, b.x, 512, M, 512, 2048, 0));
+  }
+  SAMPT_TRY(mixer_token(c, st, b.x, b.xln, w.active, w.N, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, m.lnf_w,
+                        m.lnf_b, 0));
+  SAMPT_TRY(mixer_mean(c, st, b.xln, b.xm, w.N, w.S, 512));
+  SAMPT_TRY(sgemm_nt(c, st, b.xm, 512, m.w15, 512, m.b15, nullptr, 0, b.delta, w.S * 130, w.N, w.S * 130, 512, 0));
+  SAMPT_TRY(pips_update(c, st, w, b.delta, m.gn_w, m.gn_b, m.up_w, m.up_b));
+  return 0;
+}
+
+}  // namespace sampt
+
+// One direction of PipsPointTracker._forward (pips/tracker.py:42-153).  `flip` != 0 runs the time-reversed pass on the
+// same (unflipped) feature maps by index arithmetic; traj/vis are then in flipped time order (caller flips back).
+extern "C" int sampt_pips_track(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3, int T,
+                                int H4, int W4, const float* query_points, int N, int S, int stride, float thr0, int iters,
+                                int flip, int max_windows, float* traj, float* vis, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SAMPT_CHECK(S == 8, "sampt_pips_track: S must be 8 (pips.yaml s: 8), got %d", S);
+  SAMPT_CHECK(N > 0 && T > 0, "sampt_pips_track: empty input");
+  c->ws_reset();
+  MixerW m;
+  SAMPT_TRY(load_mixer(c, &m));
+  PipsWin w{};
+  w.N = N; w.S = S; w.stride = stride; w.T = T;
+  w.pyr[0] = fmaps; w.pyr[1] = l1; w.pyr[2] = l2; w.pyr[3] = l3;
+  w.H[0] = H4; w.W[0] = W4;
+  for (int l = 1; l < 4; ++l) { w.H[l] = w.H[l - 1] / 2; w.W[l] = w.W[l - 1] / 2; }
+  int *start_d, *cur_d; uint8_t* active_d;
+  SAMPT_TRY(ws_get(c, &w.coords, (size_t)N * S * 2, "coords"));
+  SAMPT_TRY(ws_get(c, &w.ffeats, (size_t)N * S * 128, "ffeats"));
+  SAMPT_TRY(ws_get(c, &w.feat_init, (size_t)N * 128, "feat_init"));
+  SAMPT_TRY(ws_get(c, &start_d, (size_t)N, "start"));
+  SAMPT_TRY(ws_get(c, &cur_d, (size_t)N, "cur"));
+  SAMPT_TRY(ws_get(c, &active_d, (size_t)N, "active"));
+  IterBufs b;
+  const int M = N * S;
+  SAMPT_TRY(ws_get(c, &b.xin, (size_t)M * 520, "xin"));
+  SAMPT_TRY(ws_get(c, &b.x, (size_t)M * 512, "x"));
+  SAMPT_TRY(ws_get(c, &b.xln, (size_t)M * 512, "xln"));
+  SAMPT_TRY(ws_get(c, &b.h, (size_t)M * 2048, "h"));
+  SAMPT_TRY(ws_get(c, &b.xm, (size_t)N * 512, "xm"));
+  SAMPT_TRY(ws_get(c, &b.delta, (size_t)N * S * 130, "delta"));
+  w.traj = traj; w.vis = vis; w.cur = cur_d; w.active = active_d;
+  SAMPT_CUDA(cudaMemsetAsync(traj, 0, (size_t)T * N * 2 * sizeof(float), st));
+  SAMPT_CUDA(cudaMemsetAsync(vis, 0, (size_t)T * N * sizeof(float), st));
+  SAMPT_CUDA(cudaMemsetAsync(w.feat_init, 0, (size_t)N * 128 * sizeof(float), st));
+  SAMPT_CUDA(cudaMemsetAsync(b.xin, 0, (size_t)M * 520 * sizeof(float), st));
+  track_state_init_kernel<<<cdiv(N, 64), 64, 0, st>>>(query_points, traj, vis, start_d, cur_d, T, N, flip);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  SAMPT_CHECK(c->pinned_bytes >= (size_t)N * 2 * sizeof(int), "pinned scratch too small");
+  int* start_h = reinterpret_cast<int*>(c->pinned);
+  int* cur_h = start_h + N;
+  SAMPT_CUDA(cudaMemcpyAsync(start_h, start_d, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SAMPT_CUDA(cudaStreamSynchronize(st));
+  for (int n = 0; n < N; ++n) {
+    SAMPT_CHECK(start_h[n] >= 0 && start_h[n] < T, "query point %d has timestep %d outside [0,%d)", n, start_h[n], T);
+    cur_h[n] = start_h[n];
+  }
+  int windows_done = 0;
+  for (int f = 0; f < T - 1; ++f) {
+    if (max_windows > 0 && windows_done >= max_windows) break;
+    bool any = false, born = false;
+    for (int n = 0; n < N; ++n) { any |= (cur_h[n] == f); born |= (start_h[n] == f); }
+    if (!any) continue;  // pips/tracker.py:69-70
+    ++windows_done;
+    const int n_missing = std::max(0, f + S - T);
+    w.frame = f;
+    for (int s = 0; s < S; ++s) {
+      int t = std::min(f + s, T - 1);  // tail padding repeats the last frame (pips/tracker.py:73-78)
+      w.fidx[s] = flip ? (T - 1 - t) : t;
+    }
+    if (born) {  // feature-init pass: only ffeat is consumed (pips/tracker.py:81-90; the 6 mixer iterations are dead)
+      set_active_kernel<<<cdiv(N, 64), 64, 0, st>>>(start_d, f, active_d, N);
+      c->launches++;
+      w.sample_feat = 1;
+      SAMPT_TRY(pips_window_init(c, st, w));
+    }
+    set_active_kernel<<<cdiv(N, 64), 64, 0, st>>>(cur_d, f, active_d, N);
+    c->launches++;
+    w.sample_feat = 0;
+    SAMPT_TRY(pips_window_init(c, st, w));
+    for (int it = 0; it < iters; ++it) SAMPT_TRY(pips_iteration(c, st, w, m, b));
+    SAMPT_TRY(pips_link(c, st, w, m.vis_w, m.vis_b, thr0, T, n_missing));
+    SAMPT_CUDA(cudaMemcpyAsync(cur_h, cur_d, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SAMPT_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+// Unit-test entry: fused correlation lookup alone (the "first kernel").
+extern "C" int sampt_pips_corr_lookup(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3,
+                                      int S, int H4, int W4, const float* ffeats, const float* coords, int N, float* fcorr,
+                                      void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SAMPT_CHECK(S >= 1 && S <= 8, "S must be in [1,8]");
+  PipsWin w{};
+  w.N = N; w.S = S; w.stride = 4; w.T = S; w.frame = 0;
+  for (int s = 0; s < S; ++s) w.fidx[s] = s;
+  w.pyr[0] = fmaps; w.pyr[1] = l1; w.pyr[2] = l2; w.pyr[3] = l3;
+  w.H[0] = H4; w.W[0] = W4;
+  for (int l = 1; l < 4; ++l) { w.H[l] = w.H[l - 1] / 2; w.W[l] = w.W[l - 1] / 2; }
+  w.coords = const_cast<float*>(coords);
+  w.ffeats = const_cast<float*>(ffeats);
+  return pips_corr_only(c, st, w, fcorr);
+}

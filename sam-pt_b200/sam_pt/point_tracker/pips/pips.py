@@ -1,0 +1,141 @@
+"""`Pips` with the reference's constructor / forward signature and state-dict (sam_pt/point_tracker/pips/pips.py:410-620,
+SURVEY Appendix A.4) whose arithmetic runs in libsampt_b200 (csrc/pips_kernels.cu, csrc/pips_pipeline.cu)."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from sampt_b200 import native
+from sampt_b200.param_tree import build_param_tree
+
+LATENT = 128
+
+
+def _pips_shapes(S: int) -> Dict[str, Tuple[int, ...]]:
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(name, co, ci, k):
+        s[f"{name}.weight"] = (co, ci, k, k)
+        s[f"{name}.bias"] = (co,)
+
+    conv("fnet.conv1", 64, 3, 7)
+    cin = 64
+    for li, (dim, stride) in enumerate(((64, 1), (96, 2), (128, 2), (128, 2)), start=1):
+        for blk in (0, 1):
+            conv(f"fnet.layer{li}.{blk}.conv1", dim, cin if blk == 0 else dim, 3)
+            conv(f"fnet.layer{li}.{blk}.conv2", dim, dim, 3)
+        if stride != 1:
+            conv(f"fnet.layer{li}.0.downsample.0", dim, cin, 1)
+        cin = dim
+    conv("fnet.conv2", 256, 64 + 96 + 128 + 128, 3)
+    conv("fnet.conv3", LATENT, 256, 1)
+    p = "delta_block.to_delta."
+    kitchen = 4 * 7 * 7 + LATENT + 3 * 64 + 3
+    s[p + "0.weight"], s[p + "0.bias"] = (512, kitchen), (512,)
+    for l in range(1, 13):
+        for j, (a, b) in enumerate((((4 * S, S, 1), (S, 4 * S, 1)), ((2048, 512), (512, 2048)))):
+            s[f"{p}{l}.{j}.norm.weight"] = s[f"{p}{l}.{j}.norm.bias"] = (512,)
+            s[f"{p}{l}.{j}.fn.0.weight"], s[f"{p}{l}.{j}.fn.0.bias"] = a, (a[0],)
+            s[f"{p}{l}.{j}.fn.3.weight"], s[f"{p}{l}.{j}.fn.3.bias"] = b, (b[0],)
+    s[p + "13.weight"] = s[p + "13.bias"] = (512,)
+    s[p + "15.weight"], s[p + "15.bias"] = (S * (LATENT + 2), 512), (S * (LATENT + 2),)
+    s["norm.weight"] = s["norm.bias"] = (LATENT,)
+    s["ffeat_updater.0.weight"], s["ffeat_updater.0.bias"] = (LATENT, LATENT), (LATENT,)
+    s["vis_predictor.0.weight"], s["vis_predictor.0.bias"] = (1, LATENT), (1,)
+    return s
+
+
+class Pips(nn.Module):
+    """Reference signature `Pips(S=8, stride=8)` (pips.py:411)."""
+
+    def __init__(self, S=8, stride=8):
+        super().__init__()
+        self.S = S
+        self.stride = stride
+        self.hidden_dim = 256
+        self.latent_dim = LATENT
+        self.corr_levels = 4
+        self.corr_radius = 3
+        build_param_tree(self, _pips_shapes(S), seed=486124)
+        self._registered_on = None
+
+    # ------------------------------------------------------------------ weights -> kernel-native layouts
+    def native_context(self) -> native.Context:
+        dev = self.norm.weight.device
+        ctx = native.get_context(dev)
+        key = (id(ctx), tuple(p._version for p in self.parameters()), dev)
+        if self._registered_on != key:
+            sd = self.state_dict()
+            for k, v in sd.items():
+                v = v.detach().float()
+                if k.startswith("fnet.") and k.endswith(".weight") and v.dim() == 4:
+                    ctx.set_tensor(f"pips.{k}_rsck", v.permute(2, 3, 1, 0).contiguous())
+                elif k == "delta_block.to_delta.0.weight":
+                    w = torch.zeros((v.shape[0], 520), device=v.device)
+                    w[:, : v.shape[1]] = v
+                    ctx.set_tensor(f"pips.{k}_kpad", w)
+                else:
+                    ctx.set_tensor(f"pips.{k}", v.contiguous())
+            self._registered_on = key
+        return ctx
+
+    # ------------------------------------------------------------------ building blocks used by the tracker
+    def encode_frames(self, frames_u8: torch.Tensor):
+        """(T,3,H,W) uint8 -> channels-last pyramid [(T,H/4,W/4,128), /2, /4, /8] (fnet once per frame + CorrBlock pyramid)."""
+        assert frames_u8.dtype == torch.uint8 and frames_u8.is_cuda
+        if self.stride != 4:
+            raise NotImplementedError("the B200 PIPS path is built for stride 4 (configs/model/point_tracker/pips.yaml:3)")
+        ctx = self.native_context()
+        T, _, H, W = frames_u8.shape
+        H4, W4 = H // 4, W // 4
+        dev = frames_u8.device
+        pyr = [torch.empty((T, H4 >> l, W4 >> l, LATENT), device=dev, dtype=torch.float32) for l in range(4)]
+        L = native.lib()
+        native.check(L.sampt_pips_fnet(ctx.handle, native.ptr(frames_u8.contiguous()), c_int(T), c_int(H), c_int(W), c_int(4),
+                                       native.ptr(pyr[0]), native.stream_ptr()), "pips_fnet")
+        native.check(L.sampt_pips_pyramid(ctx.handle, native.ptr(pyr[0]), c_int(T), c_int(H4), c_int(W4), native.ptr(pyr[1]),
+                                          native.ptr(pyr[2]), native.ptr(pyr[3]), native.stream_ptr()), "pips_pyramid")
+        return pyr
+
+    def track(self, pyr, query_points: torch.Tensor, thr0: float, iters: int = 6, flip: bool = False,
+              max_windows: int = 0):
+        """One direction of the linked sliding-window chain. query_points (N,3) -> traj (T,N,2), vis (T,N) sigmoid."""
+        ctx = self.native_context()
+        T, H4, W4, _ = pyr[0].shape
+        N = query_points.shape[0]
+        q = query_points.detach().float().contiguous()
+        traj = torch.empty((T, N, 2), device=q.device, dtype=torch.float32)
+        vis = torch.empty((T, N), device=q.device, dtype=torch.float32)
+        native.check(native.lib().sampt_pips_track(
+            ctx.handle, native.ptr(pyr[0]), native.ptr(pyr[1]), native.ptr(pyr[2]), native.ptr(pyr[3]), c_int(T), c_int(H4),
+            c_int(W4), native.ptr(q), c_int(N), c_int(self.S), c_int(self.stride), c_float(thr0), c_int(iters),
+            c_int(1 if flip else 0), c_int(max_windows), native.ptr(traj), native.ptr(vis), native.stream_ptr()), "pips_track")
+        return traj, vis
+
+    # ------------------------------------------------------------------ reference-compatible forward
+    def forward(self, xys, rgbs, coords_init=None, feat_init=None, iters=3, trajs_g=None, vis_g=None, valids=None,
+                sw=None, return_feat=False, is_train=False):
+        """Reference `Pips.forward` (pips.py:439-620), inference subset: one S-frame window, zero-velocity init,
+        feature initialised from frame 0 (`feat_init=None`).  Returns (coord_predictions, coord_predictions2, vis_e,
+        losses=None).  The fused chain materialises only the final iteration, so every list entry is that estimate."""
+        if coords_init is not None or feat_init is not None or trajs_g is not None or is_train or self.training \
+                or return_feat:
+            raise NotImplementedError("B200 Pips.forward covers inference with coords_init=None, feat_init=None; the "
+                                      "feat_init hand-over between windows lives in sampt_pips_track")
+        B, N, _ = xys.shape
+        if B != 1:
+            raise NotImplementedError("Batch size > 1 is not supported for PIPS yet")
+        assert rgbs.shape[1] == self.S
+        frames = rgbs[0]
+        if frames.dtype != torch.uint8:
+            frames = frames.round().clamp(0, 255).to(torch.uint8)
+        pyr = self.encode_frames(frames)
+        q = torch.cat([torch.zeros((N, 1), device=xys.device), xys[0].float()], dim=1)
+        traj, vis = self.track(pyr, q, thr0=0.9, iters=iters, max_windows=1)
+        coords = traj[None]
+        vis_e = torch.logit(vis.clamp(1e-7, 1 - 1e-7))[None]
+        return [coords for _ in range(iters)], [coords for _ in range(iters + 4)], vis_e, None

@@ -1,0 +1,106 @@
+"""ctypes binding of libsampt_b200.so (include/sampt_b200.h).  This is the ONLY way the Python host code reaches the GPU
+kernels; there is no CPU or PyTorch-eager fallback: a missing library or a non-zero return code raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_size_t, c_void_p
+from typing import Dict, Optional
+
+import torch
+
+from . import build as _build
+
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.uint8: 2, torch.int32: 3, torch.bfloat16: 4}
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} is missing: the CUDA extension has not been built (run `python -c 'import __graft_entry__ as g; "
+                f"g.build()'`). There is no CPU fallback for the SAM-PT hot path.")
+        _lib = ctypes.CDLL(path)
+        _lib.sampt_last_error.restype = c_char_p
+        _lib.sampt_launch_count.restype = c_longlong
+        _lib.sampt_launch_count.argtypes = [c_void_p]
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().sampt_last_error()
+        raise RuntimeError(f"libsampt_b200 {what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "native calls take contiguous CUDA tensors"
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Context:
+    """Owns one sampt_ctx on a device, its workspace slab and references to every registered tensor."""
+
+    def __init__(self, device: torch.device, workspace_bytes: int = 4 << 30):
+        if not torch.cuda.is_available():
+            raise RuntimeError("libsampt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        self._h = c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().sampt_ctx_create(c_int(self.device.index or 0), ctypes.byref(self._h)), "ctx_create")
+        self._tensors: Dict[str, torch.Tensor] = {}
+        self._ws = None
+        self.set_workspace(workspace_bytes)
+
+    @property
+    def handle(self) -> c_void_p:
+        return self._h
+
+    def set_workspace(self, nbytes: int) -> None:
+        self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        check(lib().sampt_ctx_set_workspace(self._h, ptr(self._ws), c_size_t(nbytes)), "set_workspace")
+
+    def ensure_workspace(self, nbytes: int) -> None:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self.set_workspace(nbytes)
+
+    def set_tensor(self, name: str, t: torch.Tensor) -> None:
+        t = t.to(self.device).contiguous()
+        self._tensors[name] = t
+        dims = (c_int64 * max(t.dim(), 1))(*t.shape)
+        check(lib().sampt_set_tensor(self._h, name.encode(), ptr(t), c_int(_DTYPES[t.dtype]), c_int(t.dim()), dims),
+              f"set_tensor({name})")
+
+    def launch_count(self) -> int:
+        return int(lib().sampt_launch_count(self._h))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().sampt_ctx_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:
+            pass
+
+
+_contexts: Dict[int, Context] = {}
+
+
+def get_context(device) -> Context:
+    """One shared context per device (weights of SAM and of the tracker are registered under distinct prefixes)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"the SAM-PT B200 path runs on CUDA only (got device {device}); there is no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _contexts:
+        _contexts[idx] = Context(torch.device("cuda", idx))
+    return _contexts[idx]
