@@ -1,0 +1,777 @@
+// SAM prompt encoder + mask decoder (two-way transformer) + postprocess + on-device refinement control, strict fp32.
+// Upstream: segment_anything/modeling/{prompt_encoder,mask_decoder,transformer,sam}.py (un-vendored);
+// reference call sites sam_pt/modeling/sam_pt.py:783-828 (predict_torch x (1|2 + <=12 refinements) per frame and mask).
+//
+// Every kernel takes a `skip` flag pointer: once the refinement loop's break condition (mask area < 2 px, sam_pt.py:812)
+// has fired on the device, the remaining iterations' kernels return immediately, so the whole 13-call chain of a frame is
+// enqueued without a single host synchronisation (the reference does ~6 syncs per iteration).
+#include "common.cuh"
+#include "kernels.cuh"
+#include "../../include/sampt_b200.h"
+
+namespace sampt {
+
+#define SKIP_RETURN(skip) \
+  if ((skip) != nullptr && *(skip) != 0) return;
+
+// ------------------------------------------------------------------------------------------------------------------
+// prompt encoder, sparse part: tokens = [iou_token, mask_tokens(4) [, hq_token], points..., pad | box corners]
+// one block (256 threads = embedding channels) per prompt token
+// ------------------------------------------------------------------------------------------------------------------
+struct PromptArgs {
+  const float* coords;    // [K,2] in the 1024 input frame
+  const int* labels;      // [K]
+  int K;
+  const float* box;       // [4] or null (device)
+  int use_box;            // 1: box corners appended (and no pad point), 0: pad point appended
+  const float* gauss;     // [2,128]
+  const float* pt_emb[4]; // point_embeddings.{0..3}.weight [256]
+  const float* not_a_point;
+  const float* out_tokens; // [n_out_tok,256] iou_token ++ mask_tokens (++ hq token)
+  int n_out_tok;
+  float img_size;
+};
+
+__global__ void __launch_bounds__(256)
+prompt_tokens_kernel(PromptArgs a, float* __restrict__ tokens, const int* skip) {
+  SKIP_RETURN(skip);
+  const int t = blockIdx.x, ch = threadIdx.x;
+  float* out = tokens + (size_t)t * 256;
+  if (t < a.n_out_tok) { out[ch] = a.out_tokens[(size_t)t * 256 + ch]; return; }
+  const int i = t - a.n_out_tok;
+  float x, y;
+  int label;  // -1 pad, 0 neg, 1 pos, 2/3 box corners
+  if (i < a.K) { x = a.coords[2 * i]; y = a.coords[2 * i + 1]; label = a.labels[i]; }
+  else if (!a.use_box) { x = 0.f; y = 0.f; label = -1; }
+  else { int cidx = i - a.K; x = a.box[2 * cidx]; y = a.box[2 * cidx + 1]; label = 2 + cidx; }
+  // +0.5 (pixel centre), normalise to [0,1], 2c-1, @ G, * 2pi, [sin | cos]
+  x = (x + 0.5f) / a.img_size; y = (y + 0.5f) / a.img_size;
+  float cx = 2.f * x - 1.f, cy = 2.f * y - 1.f;
+  const int k = ch & 127;
+  float v = cx * a.gauss[k] + cy * a.gauss[128 + k];
+  v = 2.0f * 3.14159265358979323846f * v;
+  float pe = (ch < 128) ? sinf(v) : cosf(v);
+  if (label == -1) pe = a.not_a_point[ch];
+  else pe += a.pt_emb[label][ch];
+  out[ch] = pe;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// prompt encoder, dense part fused with `src = image_embedding + dense`:
+//   mask_input == null : src[tok] = feat[tok] + no_mask_embed
+//   else               : src[tok] = feat[tok] + conv1x1(GELU(LN(conv2x2s2(GELU(LN(conv2x2s2(mask)))))))
+// feat is token-major [4096,256]; one warp per token
+// ------------------------------------------------------------------------------------------------------------------
+struct DenseW {
+  const float *w0, *b0, *ln1w, *ln1b, *w3, *b3, *ln4w, *ln4b, *w6, *b6, *no_mask;
+};
+__global__ void __launch_bounds__(256)
+dense_src_kernel(const float* __restrict__ feat, const float* __restrict__ mask_in, DenseW w, float* __restrict__ src, int G,
+                 const int* skip) {
+  SKIP_RETURN(skip);
+  const int tok = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tok >= G * G) return;
+  const float* f = feat + (size_t)tok * 256;
+  float* o = src + (size_t)tok * 256;
+  if (mask_in == nullptr) {
+    for (int c = lane; c < 256; c += 32) o[c] = f[c] + w.no_mask[c];
+    return;
+  }
+  const int ty = tok / G, tx = tok % G;
+  const int MW = 4 * G;  // 256
+  // stage 1: 2x2 positions, 4 channels each (every lane computes everything: 64 MACs)
+  float h1[4][4];
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      float v[4];
+#pragma unroll
+      for (int co = 0; co < 4; ++co) v[co] = w.b0[co];
+#pragma unroll
+      for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 2; ++kx) {
+          float m = mask_in[(size_t)(ty * 4 + py * 2 + ky) * MW + tx * 4 + px * 2 + kx];
+#pragma unroll
+          for (int co = 0; co < 4; ++co) v[co] = fmaf(m, w.w0[co * 4 + ky * 2 + kx], v[co]);
+        }
+      float mean = 0.25f * (v[0] + v[1] + v[2] + v[3]);
+      float var = 0.f;
+#pragma unroll
+      for (int co = 0; co < 4; ++co) { float d = v[co] - mean; var += d * d; }
+      var *= 0.25f;
+      float rstd = 1.0f / sqrtf(var + 1e-6f);
+#pragma unroll
+      for (int co = 0; co < 4; ++co) h1[py * 2 + px][co] = gelu_erf(w.ln1w[co] * ((v[co] - mean) * rstd) + w.ln1b[co]);
+    }
+  // stage 2: conv 2x2 s2 (4 -> 16) over the 2x2 positions, LN over 16, GELU
+  float h2[16];
+  float mean = 0.f;
+#pragma unroll
+  for (int co = 0; co < 16; ++co) {
+    float v = w.b3[co];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) v = fmaf(h1[p][ci], w.w3[(co * 4 + ci) * 4 + p], v);
+    h2[co] = v;
+    mean += v;
+  }
+  mean *= (1.0f / 16.0f);
+  float var = 0.f;
+#pragma unroll
+  for (int co = 0; co < 16; ++co) { float d = h2[co] - mean; var += d * d; }
+  var *= (1.0f / 16.0f);
+  float rstd = 1.0f / sqrtf(var + 1e-6f);
+#pragma unroll
+  for (int co = 0; co < 16; ++co) h2[co] = gelu_erf(w.ln4w[co] * ((h2[co] - mean) * rstd) + w.ln4b[co]);
+  // stage 3: 1x1 conv 16 -> 256, + image embedding
+  for (int c = lane; c < 256; c += 32) {
+    float v = w.b6[c];
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) v = fmaf(h2[ci], w.w6[c * 16 + ci], v);
+    o[c] = f[c] + v;
+  }
+}
+
+// NCHW (256, G*G) -> token-major (G*G, 256)
+__global__ void nchw_to_tok_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int GG) {
+  __shared__ float tile[32][33];
+  int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32x8
+  for (int j = ty; j < 32; j += 8) tile[j][tx] = in[(size_t)(c0 + j) * GG + t0 + tx];
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) out[(size_t)(t0 + j) * C + c0 + tx] = tile[tx][j];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// row-wise helpers on small token matrices
+// ------------------------------------------------------------------------------------------------------------------
+// y = a + b (elementwise), n4 float4
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, long long n4,
+                           const int* skip) {
+  SKIP_RETURN(skip);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 u = reinterpret_cast<const float4*>(a)[i], v = reinterpret_cast<const float4*>(b)[i];
+  reinterpret_cast<float4*>(y)[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+}
+// LayerNorm over 256 channels, one warp per row: y = LN(x (+ add)) ; eps 1e-5 (nn.LayerNorm default in the transformer)
+__global__ void __launch_bounds__(256)
+ln256_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ g, const float* __restrict__ b,
+             float* __restrict__ y, int M, float eps, const int* skip) {
+  SKIP_RETURN(skip);
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = x[(size_t)row * 256 + lane + 32 * i];
+    if (add) v[i] += add[(size_t)row * 256 + lane + 32 * i];
+    s += v[i];
+  }
+  float mean = warp_sum(s) * (1.0f / 256.0f);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { float d = v[i] - mean; sq += d * d; }
+  float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / 256.0f) + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = lane + 32 * i;
+    y[(size_t)row * 256 + c] = (v[i] - mean) * rstd * g[c] + b[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// attention cores (projections are done with sgemm_nt)
+// ------------------------------------------------------------------------------------------------------------------
+// tokens attend: q [T, H*dh], k/v [Nk, H*dh]; out [T, H*dh].  One block per (token, head); Nk up to 4096 (+ small T case).
+template <int DH>
+__global__ void __launch_bounds__(256)
+attn_q_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, float* __restrict__ out,
+                    int Nk, int H, const int* skip) {
+  SKIP_RETURN(skip);
+  const int t = blockIdx.x, h = blockIdx.y;
+  const int ld = H * DH;
+  __shared__ float sq[DH];
+  __shared__ float red[32];
+  __shared__ float sacc[8][DH];
+  if (threadIdx.x < DH) sq[threadIdx.x] = q[(size_t)t * ld + h * DH + threadIdx.x];
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)DH);
+  // pass 1: max
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < Nk; j += 256) {
+    const float* kp = k + (size_t)j * ld + h * DH;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) s = fmaf(sq[d], kp[d], s);
+    mx = fmaxf(mx, s * scale);
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float m = threadIdx.x < 8 ? red[threadIdx.x] : -INFINITY;
+    m = warp_max(m);
+    if (threadIdx.x == 0) red[0] = m;
+  }
+  __syncthreads();
+  mx = red[0];
+  __syncthreads();
+  // pass 2: exp, sum, weighted V
+  float acc[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+  float lsum = 0.f;
+  for (int j = threadIdx.x; j < Nk; j += 256) {
+    const float* kp = k + (size_t)j * ld + h * DH;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) s = fmaf(sq[d], kp[d], s);
+    float p = expf(s * scale - mx);
+    lsum += p;
+    const float* vp = v + (size_t)j * ld + h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, vp[d], acc[d]);
+  }
+  lsum = block_sum(lsum, red);
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = warp_sum(acc[d]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < DH; ++d) sacc[threadIdx.x >> 5][d] = acc[d];
+  }
+  __syncthreads();
+  if (threadIdx.x < DH) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += sacc[w][threadIdx.x];
+    out[(size_t)t * ld + h * DH + threadIdx.x] = a / lsum;
+  }
+}
+
+// image tokens attend to the (few) prompt tokens: q [N, H*DH], k/v [T, H*DH], T <= 512.  One thread per (image token, head).
+template <int DH>
+__global__ void __launch_bounds__(256)
+attn_kv_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, float* __restrict__ out,
+                     int N, int T, int H, const int* skip) {
+  SKIP_RETURN(skip);
+  extern __shared__ float skv[];  // k [T][H*DH], v [T][H*DH]
+  const int ld = H * DH;
+  for (int i = threadIdx.x; i < T * ld; i += 256) { skv[i] = k[i]; skv[T * ld + i] = v[i]; }
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)N * H) return;
+  const int n = (int)(idx / H), h = (int)(idx % H);
+  float qv[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) qv[d] = q[(size_t)n * ld + h * DH + d];
+  const float scale = 1.0f / sqrtf((float)DH);
+  float mx = -INFINITY;
+  for (int t = 0; t < T; ++t) {
+    const float* kp = skv + t * ld + h * DH;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) s = fmaf(qv[d], kp[d], s);
+    mx = fmaxf(mx, s * scale);
+  }
+  float acc[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+  float lsum = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float* kp = skv + t * ld + h * DH;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) s = fmaf(qv[d], kp[d], s);
+    float p = expf(s * scale - mx);
+    lsum += p;
+    const float* vp = skv + T * ld + t * ld + h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, vp[d], acc[d]);
+  }
+  float inv = 1.0f / lsum;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) out[(size_t)n * ld + h * DH + d] = acc[d] * inv;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// heads: 3-layer MLPs (ReLU) on single token rows: block b -> job b
+// ------------------------------------------------------------------------------------------------------------------
+struct Mlp3Job { const float* x; const float *w0, *b0, *w1, *b1, *w2, *b2; int n_out; float* y; };
+struct Mlp3Jobs { Mlp3Job j[8]; };
+__global__ void __launch_bounds__(256)
+mlp3_kernel(Mlp3Jobs jobs, const int* skip) {
+  SKIP_RETURN(skip);
+  const Mlp3Job& J = jobs.j[blockIdx.x];
+  __shared__ float a[256], b[256];
+  const int t = threadIdx.x;
+  a[t] = J.x[t];
+  __syncthreads();
+  float s = J.b0[t];
+  for (int k = 0; k < 256; ++k) s = fmaf(J.w0[t * 256 + k], a[k], s);
+  b[t] = fmaxf(s, 0.f);
+  __syncthreads();
+  s = J.b1[t];
+  for (int k = 0; k < 256; ++k) s = fmaf(J.w1[t * 256 + k], b[k], s);
+  __syncthreads();
+  a[t] = fmaxf(s, 0.f);
+  __syncthreads();
+  if (t < J.n_out) {
+    s = J.b2[t];
+    for (int k = 0; k < 256; ++k) s = fmaf(J.w2[t * 256 + k], a[k], s);
+    J.y[t] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// output upscaling tail fused with the hyper-network dot product:
+//   up1 = ConvT(256->64,k2,s2)(src) was produced by a GEMM as u1[tok][(dy*2+dx)*64 + c]  (128x128 pixels x 64 ch)
+//   low_res[m][Y][X] = sum_c hyper[m][c] * GELU( ConvT(64->32,k2,s2)( GELU(LN2d(up1)) ) )[c][Y][X]
+// one thread per low-res output pixel (256x256)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+upscale_mask_kernel(const float* __restrict__ u1, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                    const float* __restrict__ w2 /*[64][32][2][2]*/, const float* __restrict__ b2, const float* __restrict__ hyper,
+                    int n_masks, float* __restrict__ low_res, int G, const int* skip) {
+  SKIP_RETURN(skip);
+  __shared__ float sw[64 * 32 * 4];
+  __shared__ float sh[4 * 32];
+  for (int i = threadIdx.x; i < 64 * 32 * 4; i += 256) sw[i] = w2[i];
+  if (threadIdx.x < n_masks * 32) sh[threadIdx.x] = hyper[threadIdx.x];
+  __syncthreads();
+  const int R = 4 * G;  // 256
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= R * R) return;
+  const int Y = pix / R, X = pix % R;
+  const int y2 = Y >> 1, x2 = X >> 1, dy2 = Y & 1, dx2 = X & 1;        // position in the 128x128 map + sub-pixel
+  const int ty = y2 >> 1, tx = x2 >> 1, dy1 = y2 & 1, dx1 = x2 & 1;    // token + sub-pixel of the first ConvT
+  const float* p = u1 + ((size_t)(ty * G + tx)) * 256 + (dy1 * 2 + dx1) * 64;
+  float v[64];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; c += 4) {
+    float4 t = *reinterpret_cast<const float4*>(p + c);
+    v[c] = t.x; v[c + 1] = t.y; v[c + 2] = t.z; v[c + 3] = t.w;
+    s += t.x + t.y + t.z + t.w;
+  }
+  float mean = s * (1.0f / 64.0f);
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; ++c) { float d = v[c] - mean; sq += d * d; }
+  float rstd = 1.0f / sqrtf(sq * (1.0f / 64.0f) + 1e-6f);
+#pragma unroll
+  for (int c = 0; c < 64; ++c) v[c] = gelu_erf(lnw[c] * ((v[c] - mean) * rstd) + lnb[c]);
+  float outm[4] = {0.f, 0.f, 0.f, 0.f};
+  const int sub = dy2 * 2 + dx2;
+  for (int co = 0; co < 32; ++co) {
+    float a = b2[co];
+#pragma unroll
+    for (int ci = 0; ci < 64; ++ci) a = fmaf(v[ci], sw[(ci * 32 + co) * 4 + sub], a);
+    a = gelu_erf(a);
+    for (int m = 0; m < n_masks; ++m) outm[m] = fmaf(sh[m * 32 + co], a, outm[m]);
+  }
+  for (int m = 0; m < n_masks; ++m) low_res[(size_t)m * R * R + pix] = outm[m];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sam.postprocess_masks fused: bilinear (align_corners=False) 256^2 -> 1024^2, crop [:in_h,:in_w], bilinear -> (H,W);
+// + bounding box / area of (logit > 0) for the refinement loop (sam_pt.py:811-820)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l1) {
+  float s = scale * ((float)dst + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  l1 = s - (float)i0;
+}
+__device__ __forceinline__ float up4_sample(const float* __restrict__ lr, int R, int S, int y, int x) {
+  // value of the (virtual) S x S up-sampled map at integer (y, x)
+  const float sc = (float)R / (float)S;
+  int y0, y1, x0, x1; float ly, lx;
+  src_index(sc, y, R, y0, y1, ly);
+  src_index(sc, x, R, x0, x1, lx);
+  float hy = 1.f - ly, hx = 1.f - lx;
+  return hy * (hx * lr[y0 * R + x0] + lx * lr[y0 * R + x1]) + ly * (hx * lr[y1 * R + x0] + lx * lr[y1 * R + x1]);
+}
+__global__ void __launch_bounds__(256)
+postprocess_kernel(const float* __restrict__ low_res, int n_masks, int R, int S, int in_h, int in_w, int H, int W,
+                   float* __restrict__ out, int* __restrict__ bbox /*[5]: xmin ymin xmax ymax count (mask 0)*/, const int* skip) {
+  SKIP_RETURN(skip);
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long HW = (long long)H * W;
+  int xmin = 0x7fffffff, ymin = 0x7fffffff, xmax = -1, ymax = -1, cnt = 0;
+  if (i < HW * n_masks) {
+    const int m = (int)(i / HW);
+    const int y = (int)((i % HW) / W), x = (int)(i % W);
+    const float* lr = low_res + (size_t)m * R * R;
+    const float sy = (float)in_h / (float)H, sx = (float)in_w / (float)W;
+    int y0, y1, x0, x1; float ly, lx;
+    src_index(sy, y, in_h, y0, y1, ly);
+    src_index(sx, x, in_w, x0, x1, lx);
+    float hy = 1.f - ly, hx = 1.f - lx;
+    float v = hy * (hx * up4_sample(lr, R, S, y0, x0) + lx * up4_sample(lr, R, S, y0, x1)) +
+              ly * (hx * up4_sample(lr, R, S, y1, x0) + lx * up4_sample(lr, R, S, y1, x1));
+    out[i] = v;
+    if (m == 0 && v > 0.f) { xmin = xmax = x; ymin = ymax = y; cnt = 1; }
+  }
+  if (bbox) {
+    // block reduce then 5 atomics per block
+    __shared__ int sred[5][8];
+    for (int o = 16; o > 0; o >>= 1) {
+      xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+      ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+      xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+      ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sred[0][w] = xmin; sred[1][w] = ymin; sred[2][w] = xmax; sred[3][w] = ymax; sred[4][w] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < 8; ++k) {
+        sred[0][0] = min(sred[0][0], sred[0][k]); sred[1][0] = min(sred[1][0], sred[1][k]);
+        sred[2][0] = max(sred[2][0], sred[2][k]); sred[3][0] = max(sred[3][0], sred[3][k]);
+        sred[4][0] += sred[4][k];
+      }
+      if (sred[4][0] > 0) {
+        atomicMin(&bbox[0], sred[0][0]); atomicMin(&bbox[1], sred[1][0]);
+        atomicMax(&bbox[2], sred[2][0]); atomicMax(&bbox[3], sred[3][0]);
+        atomicAdd(&bbox[4], sred[4][0]);
+      }
+    }
+  }
+}
+// refinement control (sam_pt.py:810-820): count<2 -> stop; else box = (xmin,ymin,xmax,ymax) in ORIGINAL pixels (the
+// reference passes it to predict_torch without apply_boxes); resets the accumulators for the next call.
+__global__ void refine_ctl_kernel(int* bbox, float* box_out, int* skip, int* n_done) {
+  if (*skip == 0) {
+    if (bbox[4] < 2) *skip = 1;
+    else {
+      box_out[0] = (float)bbox[0]; box_out[1] = (float)bbox[1]; box_out[2] = (float)bbox[2]; box_out[3] = (float)bbox[3];
+      if (n_done) *n_done += 1;
+    }
+  }
+  bbox[0] = 0x7fffffff; bbox[1] = 0x7fffffff; bbox[2] = -1; bbox[3] = -1; bbox[4] = 0;
+}
+__global__ void init_ctl_kernel(int* bbox, int* skip, int* n_done) {
+  bbox[0] = 0x7fffffff; bbox[1] = 0x7fffffff; bbox[2] = -1; bbox[3] = -1; bbox[4] = 0;
+  *skip = 0;
+  if (n_done) *n_done = 0;
+}
+
+// ====================================================================================================================
+// host orchestration
+// ====================================================================================================================
+struct AttnW { const float *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob; int internal; };
+struct LayerW {
+  AttnW self_attn, t2i, i2t;
+  const float *n1w, *n1b, *n2w, *n2b, *n3w, *n3b, *n4w, *n4b;
+  const float *l1w, *l1b, *l2w, *l2b;
+  const float *pek_t2i, *peq_i2t;  // key_pe @ Wk^T (t2i) and key_pe @ Wq^T (i2t): constant, precomputed at load time
+};
+struct DecW {
+  LayerW layer[2];
+  AttnW final_attn; const float *nfw, *nfb, *pek_final;
+  const float *up0_w /*[256 tok-in][4*64]^T as [4*64][256]*/, *up0_b4 /*[256] bias tiled over the 4 sub-pixels*/;
+  const float *up_lnw, *up_lnb, *up3_w, *up3_b;
+  Mlp3Job hyper[4], iou;
+  DenseW dense;
+  PromptArgs prompt;
+  int n_out_tok;
+};
+
+static int load_attn(Ctx* c, const std::string& p, AttnW* a, int internal) {
+  a->internal = internal;
+  SAMPT_TRY(get_f32(c, p + "q_proj.weight", &a->qw)); SAMPT_TRY(get_f32(c, p + "q_proj.bias", &a->qb));
+  SAMPT_TRY(get_f32(c, p + "k_proj.weight", &a->kw)); SAMPT_TRY(get_f32(c, p + "k_proj.bias", &a->kb));
+  SAMPT_TRY(get_f32(c, p + "v_proj.weight", &a->vw)); SAMPT_TRY(get_f32(c, p + "v_proj.bias", &a->vb));
+  SAMPT_TRY(get_f32(c, p + "out_proj.weight", &a->ow)); SAMPT_TRY(get_f32(c, p + "out_proj.bias", &a->ob));
+  return 0;
+}
+static int load_mlp3(Ctx* c, const std::string& p, Mlp3Job* j, int n_out) {
+  SAMPT_TRY(get_f32(c, p + "layers.0.weight", &j->w0)); SAMPT_TRY(get_f32(c, p + "layers.0.bias", &j->b0));
+  SAMPT_TRY(get_f32(c, p + "layers.1.weight", &j->w1)); SAMPT_TRY(get_f32(c, p + "layers.1.bias", &j->b1));
+  SAMPT_TRY(get_f32(c, p + "layers.2.weight", &j->w2)); SAMPT_TRY(get_f32(c, p + "layers.2.bias", &j->b2));
+  j->n_out = n_out;
+  return 0;
+}
+static int load_dec(Ctx* c, DecW* w) {
+  const std::string md = "sam.mask_decoder.", tr = md + "transformer.", pe = "sam.prompt_encoder.";
+  for (int i = 0; i < 2; ++i) {
+    const std::string lp = tr + "layers." + std::to_string(i) + ".";
+    LayerW& L = w->layer[i];
+    SAMPT_TRY(load_attn(c, lp + "self_attn.", &L.self_attn, 256));
+    SAMPT_TRY(load_attn(c, lp + "cross_attn_token_to_image.", &L.t2i, 128));
+    SAMPT_TRY(load_attn(c, lp + "cross_attn_image_to_token.", &L.i2t, 128));
+    SAMPT_TRY(get_f32(c, lp + "norm1.weight", &L.n1w)); SAMPT_TRY(get_f32(c, lp + "norm1.bias", &L.n1b));
+    SAMPT_TRY(get_f32(c, lp + "norm2.weight", &L.n2w)); SAMPT_TRY(get_f32(c, lp + "norm2.bias", &L.n2b));
+    SAMPT_TRY(get_f32(c, lp + "norm3.weight", &L.n3w)); SAMPT_TRY(get_f32(c, lp + "norm3.bias", &L.n3b));
+    SAMPT_TRY(get_f32(c, lp + "norm4.weight", &L.n4w)); SAMPT_TRY(get_f32(c, lp + "norm4.bias", &L.n4b));
+    SAMPT_TRY(get_f32(c, lp + "mlp.lin1.weight", &L.l1w)); SAMPT_TRY(get_f32(c, lp + "mlp.lin1.bias", &L.l1b));
+    SAMPT_TRY(get_f32(c, lp + "mlp.lin2.weight", &L.l2w)); SAMPT_TRY(get_f32(c, lp + "mlp.lin2.bias", &L.l2b));
+    SAMPT_TRY(get_f32(c, lp + "pek_t2i", &L.pek_t2i)); SAMPT_TRY(get_f32(c, lp + "peq_i2t", &L.peq_i2t));
+  }
+  SAMPT_TRY(load_attn(c, tr + "final_attn_token_to_image.", &w->final_attn, 128));
+  SAMPT_TRY(get_f32(c, tr + "norm_final_attn.weight", &w->nfw)); SAMPT_TRY(get_f32(c, tr + "norm_final_attn.bias", &w->nfb));
+  SAMPT_TRY(get_f32(c, tr + "pek_final", &w->pek_final));
+  SAMPT_TRY(get_f32(c, md + "output_upscaling.0.weight_gemm", &w->up0_w));
+  SAMPT_TRY(get_f32(c, md + "output_upscaling.0.bias4", &w->up0_b4));
+  SAMPT_TRY(get_f32(c, md + "output_upscaling.1.weight", &w->up_lnw)); SAMPT_TRY(get_f32(c, md + "output_upscaling.1.bias", &w->up_lnb));
+  SAMPT_TRY(get_f32(c, md + "output_upscaling.3.weight", &w->up3_w)); SAMPT_TRY(get_f32(c, md + "output_upscaling.3.bias", &w->up3_b));
+  for (int i = 0; i < 4; ++i) SAMPT_TRY(load_mlp3(c, md + "output_hypernetworks_mlps." + std::to_string(i) + ".", &w->hyper[i], 32));
+  SAMPT_TRY(load_mlp3(c, md + "iou_prediction_head.", &w->iou, 4));
+  DenseW& d = w->dense;
+  SAMPT_TRY(get_f32(c, pe + "mask_downscaling.0.weight", &d.w0)); SAMPT_TRY(get_f32(c, pe + "mask_downscaling.0.bias", &d.b0));
+  SAMPT_TRY(get_f32(c, pe + "mask_downscaling.1.weight", &d.ln1w)); SAMPT_TRY(get_f32(c, pe + "mask_downscaling.1.bias", &d.ln1b));
+  SAMPT_TRY(get_f32(c, pe + "mask_downscaling.3.weight", &d.w3)); SAMPT_TRY(get_f32(c, pe + "mask_downscaling.3.bias", &d.b3));
+  SAMPT_TRY(get_f32(c, pe + "mask_downscaling.4.weight", &d.ln4w)); SAMPT_TRY(get_f32(c, pe + "mask_downscaling.4.bias", &d.ln4b));
+  SAMPT_TRY(get_f32(c, pe + "mask_downscaling.6.weight", &d.w6)); SAMPT_TRY(get_f32(c, pe + "mask_downscaling.6.bias", &d.b6));
+  SAMPT_TRY(get_f32(c, pe + "no_mask_embed.weight", &d.no_mask));
+  PromptArgs& pa = w->prompt;
+  SAMPT_TRY(get_f32(c, pe + "pe_layer.positional_encoding_gaussian_matrix", &pa.gauss));
+  for (int i = 0; i < 4; ++i) SAMPT_TRY(get_f32(c, pe + "point_embeddings." + std::to_string(i) + ".weight", &pa.pt_emb[i]));
+  SAMPT_TRY(get_f32(c, pe + "not_a_point_embed.weight", &pa.not_a_point));
+  SAMPT_TRY(get_f32(c, md + "output_tokens", &pa.out_tokens));
+  const TensorRef* ot = c->find(md + "output_tokens");
+  pa.n_out_tok = (int)ot->dims[0];
+  w->n_out_tok = pa.n_out_tok;
+  return 0;
+}
+
+struct DecBufs {
+  float *tokens, *queries, *qpe, *tq, *tk, *tv, *ta, *tmp, *mlp_h;   // token side  (T rows)
+  float *src, *keys, *ik, *iv, *iq, *ia;                            // image side  (4096 rows)
+  float *u1, *hyper, *iou4;
+  int T;
+};
+
+#define LAUNCH_OK() do { c->launches++; SAMPT_LAUNCH_CHECK(); } while (0)
+
+static int sg(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, const float* b, const float* resid, int ldr,
+              float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
+  return sgemm_nt_skip(c, st, X, ldx, W, K, b, resid, ldr, Y, ldy, M, N, K, act, skip);
+}
+
+// tokens -> image attention: queries attend over the 4096 image tokens.  q_in already includes the query PE.
+static int attn_tok_to_img(Ctx* c, cudaStream_t st, const AttnW& a, const float* q_in, const float* keys, const float* pek,
+                           DecBufs& b, float* out /*[T,256]*/, const float* resid, int GG, const int* skip) {
+  const int T = b.T;
+  SAMPT_TRY(sg(c, st, q_in, 256, a.qw, a.qb, nullptr, 0, b.tq, 128, T, 128, 256, 0, skip));
+  SAMPT_TRY(sg(c, st, keys, 256, a.kw, a.kb, pek, 128, b.ik, 128, GG, 128, 256, 0, skip));   // (keys + key_pe) Wk^T
+  SAMPT_TRY(sg(c, st, keys, 256, a.vw, a.vb, nullptr, 0, b.iv, 128, GG, 128, 256, 0, skip));
+  attn_q_small_kernel<16><<<dim3(T, 8), 256, 0, st>>>(b.tq, b.ik, b.iv, b.ta, GG, 8, skip);
+  LAUNCH_OK();
+  SAMPT_TRY(sg(c, st, b.ta, 128, a.ow, a.ob, resid, 256, out, 256, T, 256, 128, 0, skip));
+  return 0;
+}
+
+static int two_way_layer(Ctx* c, cudaStream_t st, const LayerW& L, int idx, DecBufs& b, int GG, const int* skip) {
+  const int T = b.T;
+  // (1) self attention on the prompt tokens
+  if (idx == 0) {
+    SAMPT_TRY(sg(c, st, b.queries, 256, L.self_attn.qw, L.self_attn.qb, nullptr, 0, b.tq, 256, T, 256, 256, 0, skip));
+    SAMPT_TRY(sg(c, st, b.queries, 256, L.self_attn.kw, L.self_attn.kb, nullptr, 0, b.tk, 256, T, 256, 256, 0, skip));
+  } else {
+    add_kernel<<<cdiv(T * 64, 256), 256, 0, st>>>(b.queries, b.tokens, b.qpe, (long long)T * 64, skip);
+    LAUNCH_OK();
+    SAMPT_TRY(sg(c, st, b.qpe, 256, L.self_attn.qw, L.self_attn.qb, nullptr, 0, b.tq, 256, T, 256, 256, 0, skip));
+    SAMPT_TRY(sg(c, st, b.qpe, 256, L.self_attn.kw, L.self_attn.kb, nullptr, 0, b.tk, 256, T, 256, 256, 0, skip));
+  }
+  SAMPT_TRY(sg(c, st, b.queries, 256, L.self_attn.vw, L.self_attn.vb, nullptr, 0, b.tv, 256, T, 256, 256, 0, skip));
+  attn_q_small_kernel<32><<<dim3(T, 8), 256, 0, st>>>(b.tq, b.tk, b.tv, b.ta, T, 8, skip);
+  LAUNCH_OK();
+  // layer 0 replaces the queries, later layers add (upstream skip_first_layer_pe)
+  SAMPT_TRY(sg(c, st, b.ta, 256, L.self_attn.ow, L.self_attn.ob, idx == 0 ? nullptr : b.queries, 256, b.tmp, 256, T, 256, 256, 0, skip));
+  ln256_kernel<<<cdiv(T, 8), 256, 0, st>>>(b.tmp, nullptr, L.n1w, L.n1b, b.queries, T, 1e-5f, skip);
+  LAUNCH_OK();
+  // (2) cross attention tokens -> image
+  add_kernel<<<cdiv(T * 64, 256), 256, 0, st>>>(b.queries, b.tokens, b.qpe, (long long)T * 64, skip);
+  LAUNCH_OK();
+  SAMPT_TRY(attn_tok_to_img(c, st, L.t2i, b.qpe, b.keys, L.pek_t2i, b, b.tmp, b.queries, GG, skip));
+  ln256_kernel<<<cdiv(T, 8), 256, 0, st>>>(b.tmp, nullptr, L.n2w, L.n2b, b.queries, T, 1e-5f, skip);
+  LAUNCH_OK();
+  // (3) MLP
+  SAMPT_TRY(sg(c, st, b.queries, 256, L.l1w, L.l1b, nullptr, 0, b.mlp_h, 2048, T, 2048, 256, 2, skip));
+  SAMPT_TRY(sg(c, st, b.mlp_h, 2048, L.l2w, L.l2b, b.queries, 256, b.tmp, 256, T, 256, 2048, 0, skip));
+  ln256_kernel<<<cdiv(T, 8), 256, 0, st>>>(b.tmp, nullptr, L.n3w, L.n3b, b.queries, T, 1e-5f, skip);
+  LAUNCH_OK();
+  // (4) cross attention image -> tokens
+  add_kernel<<<cdiv(T * 64, 256), 256, 0, st>>>(b.queries, b.tokens, b.qpe, (long long)T * 64, skip);
+  LAUNCH_OK();
+  SAMPT_TRY(sg(c, st, b.keys, 256, L.i2t.qw, L.i2t.qb, L.peq_i2t, 128, b.iq, 128, GG, 128, 256, 0, skip));  // (keys+pe) Wq^T
+  SAMPT_TRY(sg(c, st, b.qpe, 256, L.i2t.kw, L.i2t.kb, nullptr, 0, b.tk, 128, T, 128, 256, 0, skip));
+  SAMPT_TRY(sg(c, st, b.queries, 256, L.i2t.vw, L.i2t.vb, nullptr, 0, b.tv, 128, T, 128, 256, 0, skip));
+  {
+    size_t smem = (size_t)2 * T * 128 * sizeof(float);
+    SAMPT_CHECK(smem <= 200 * 1024, "too many prompt tokens (%d) for the image->token attention kernel", T);
+    static size_t set = 0;
+    if (smem > set) {
+      SAMPT_CUDA(cudaFuncSetAttribute(attn_kv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      set = 200 * 1024;
+    }
+    attn_kv_small_kernel<16><<<cdiv((long long)GG * 8, 256), 256, smem, st>>>(b.iq, b.tk, b.tv, b.ia, GG, T, 8, skip);
+    LAUNCH_OK();
+  }
+  SAMPT_TRY(sg(c, st, b.ia, 128, L.i2t.ow, L.i2t.ob, b.keys, 256, b.src, 256, GG, 256, 128, 0, skip));   // keys + attn_out
+  ln256_kernel<<<cdiv(GG, 8), 256, 0, st>>>(b.src, nullptr, L.n4w, L.n4b, b.keys, GG, 1e-5f, skip);
+  LAUNCH_OK();
+  return 0;
+}
+
+struct DecodeCall {
+  const float* feat_tok;     // [GG,256] token-major image embedding
+  const float* coords; const int* labels; int K;
+  const float* box; int use_box;
+  const float* mask_in;      // [256*256] or null
+  int n_masks, tok0;         // output masks = mask tokens [tok0, tok0+n_masks)
+  int in_h, in_w, H, W;
+  float* logits;             // [n_masks, H, W]
+  float* iou;                // [n_masks]
+  float* low_res;            // [n_masks, 256, 256]
+  int* bbox;                 // [5] or null
+  const int* skip;
+};
+
+static int decode_once(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, const DecodeCall& d, int G) {
+  const int GG = G * G;
+  const int T = w.n_out_tok + d.K + (d.use_box ? 2 : 1);
+  b.T = T;
+  PromptArgs pa = w.prompt;
+  pa.coords = d.coords; pa.labels = d.labels; pa.K = d.K; pa.box = d.box; pa.use_box = d.use_box; pa.img_size = (float)(G * 16);
+  prompt_tokens_kernel<<<T, 256, 0, st>>>(pa, b.tokens, d.skip);
+  LAUNCH_OK();
+  dense_src_kernel<<<cdiv(GG, 8), 256, 0, st>>>(d.feat_tok, d.mask_in, w.dense, b.keys, G, d.skip);
+  LAUNCH_OK();
+  SAMPT_CUDA(cudaMemcpyAsync(b.queries, b.tokens, (size_t)T * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < 2; ++i) SAMPT_TRY(two_way_layer(c, st, w.layer[i], i, b, GG, d.skip));
+  // final token -> image attention
+  add_kernel<<<cdiv(T * 64, 256), 256, 0, st>>>(b.queries, b.tokens, b.qpe, (long long)T * 64, d.skip);
+  LAUNCH_OK();
+  SAMPT_TRY(attn_tok_to_img(c, st, w.final_attn, b.qpe, b.keys, w.pek_final, b, b.tmp, b.queries, GG, d.skip));
+  ln256_kernel<<<cdiv(T, 8), 256, 0, st>>>(b.tmp, nullptr, w.nfw, w.nfb, b.queries, T, 1e-5f, d.skip);
+  LAUNCH_OK();
+  // heads
+  Mlp3Jobs jobs{};
+  for (int m = 0; m < d.n_masks; ++m) {
+    jobs.j[m] = w.hyper[d.tok0 + m];
+    jobs.j[m].x = b.queries + (size_t)(1 + d.tok0 + m) * 256;
+    jobs.j[m].y = b.hyper + m * 32;
+  }
+  jobs.j[d.n_masks] = w.iou;
+  jobs.j[d.n_masks].x = b.queries;
+  jobs.j[d.n_masks].y = b.iou4;
+  mlp3_kernel<<<d.n_masks + 1, 256, 0, st>>>(jobs, d.skip);
+  LAUNCH_OK();
+  // upscaling: ConvT(256->64) as GEMM [GG,256] x [256(4 sub-pixels x 64), 256]^T, then fused LN+GELU+ConvT+GELU+hyper dot
+  SAMPT_TRY(sg(c, st, b.keys, 256, w.up0_w, w.up0_b4, nullptr, 0, b.u1, 256, GG, 256, 256, 0, d.skip));
+  upscale_mask_kernel<<<cdiv(16 * GG, 256), 256, 0, st>>>(b.u1, w.up_lnw, w.up_lnb, w.up3_w, w.up3_b, b.hyper, d.n_masks, d.low_res,
+                                                         G, d.skip);
+  LAUNCH_OK();
+  postprocess_kernel<<<cdiv((long long)d.n_masks * d.H * d.W, 256), 256, 0, st>>>(d.low_res, d.n_masks, 4 * G, 16 * G, d.in_h, d.in_w,
+                                                                                 d.H, d.W, d.logits, d.bbox, d.skip);
+  LAUNCH_OK();
+  // iou predictions of the selected tokens
+  SAMPT_CUDA(cudaMemcpyAsync(d.iou, b.iou4 + d.tok0, d.n_masks * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int alloc_dec_bufs(Ctx* c, DecBufs* b, int Tmax, int GG) {
+  SAMPT_TRY(ws_get(c, &b->tokens, (size_t)Tmax * 256, "dec tokens"));
+  SAMPT_TRY(ws_get(c, &b->queries, (size_t)Tmax * 256, "dec queries"));
+  SAMPT_TRY(ws_get(c, &b->qpe, (size_t)Tmax * 256, "dec qpe"));
+  SAMPT_TRY(ws_get(c, &b->tq, (size_t)Tmax * 256, "dec tq"));
+  SAMPT_TRY(ws_get(c, &b->tk, (size_t)Tmax * 256, "dec tk"));
+  SAMPT_TRY(ws_get(c, &b->tv, (size_t)Tmax * 256, "dec tv"));
+  SAMPT_TRY(ws_get(c, &b->ta, (size_t)Tmax * 256, "dec ta"));
+  SAMPT_TRY(ws_get(c, &b->tmp, (size_t)Tmax * 256, "dec tmp"));
+  SAMPT_TRY(ws_get(c, &b->mlp_h, (size_t)Tmax * 2048, "dec mlp"));
+  SAMPT_TRY(ws_get(c, &b->src, (size_t)GG * 256, "dec src"));
+  SAMPT_TRY(ws_get(c, &b->keys, (size_t)GG * 256, "dec keys"));
+  SAMPT_TRY(ws_get(c, &b->ik, (size_t)GG * 128, "dec ik"));
+  SAMPT_TRY(ws_get(c, &b->iv, (size_t)GG * 128, "dec iv"));
+  SAMPT_TRY(ws_get(c, &b->iq, (size_t)GG * 128, "dec iq"));
+  SAMPT_TRY(ws_get(c, &b->ia, (size_t)GG * 128, "dec ia"));
+  SAMPT_TRY(ws_get(c, &b->u1, (size_t)GG * 256, "dec u1"));
+  SAMPT_TRY(ws_get(c, &b->hyper, (size_t)4 * 32, "dec hyper"));
+  SAMPT_TRY(ws_get(c, &b->iou4, (size_t)8, "dec iou"));
+  return 0;
+}
+
+}  // namespace sampt
+
+using namespace sampt;
+
+extern "C" int sampt_sam_features_to_tokens(sampt_ctx* ctx, const float* feat_nchw, float* feat_tok, int C, int GG, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  SAMPT_CHECK(C % 32 == 0 && GG % 32 == 0, "features_to_tokens: C and G*G must be multiples of 32");
+  nchw_to_tok_kernel<<<dim3(GG / 32, C / 32), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(feat_nchw, feat_tok, C, GG);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  return 0;
+}
+
+// SamPredictor.predict_torch (one call): prompt encoder + mask decoder + postprocess_masks.
+extern "C" int sampt_sam_predict(sampt_ctx* ctx, const float* feat_tok, int G, const float* coords, const int* labels, int K,
+                                 const float* box, const float* mask_input, int multimask, int in_h, int in_w, int H, int W,
+                                 float* logits, float* iou, float* low_res, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  c->ws_reset();
+  DecW w;
+  SAMPT_TRY(load_dec(c, &w));
+  DecBufs b;
+  SAMPT_TRY(alloc_dec_bufs(c, &b, w.n_out_tok + K + 2, G * G));
+  DecodeCall d{};
+  d.feat_tok = feat_tok; d.coords = coords; d.labels = labels; d.K = K; d.box = box; d.use_box = box ? 1 : 0;
+  d.mask_in = mask_input; d.n_masks = multimask ? 3 : 1; d.tok0 = multimask ? 1 : 0;
+  d.in_h = in_h; d.in_w = in_w; d.H = H; d.W = W; d.logits = logits; d.iou = iou; d.low_res = low_res; d.bbox = nullptr; d.skip = nullptr;
+  return decode_once(c, st, w, b, d, G);
+}
+
+// SamPt.predict_mask (sam_pt.py:760-837) for negative_points_per_mask == 0 or > 0, with the iterative box refinement
+// loop run entirely on the device.  coords/labels: visible points already mapped by apply_coords (1024 frame).
+// n_pos_first: if > 0, a first call uses only the first n_pos_first (positive) points and feeds its low-res mask to the
+// second call (sam_pt.py:792-807); 0 = single initial call (:783-790).
+// outputs: logits [H,W], iou [1], low_res [256,256], n_refine_done [1] (int, device).
+extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const float* coords, const int* labels, int K,
+                                        const float* pos_coords, const int* pos_labels, int n_pos_first, int n_refine, int in_h,
+                                        int in_w, int H, int W, float* logits, float* iou, float* low_res, int* n_refine_done,
+                                        void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  c->ws_reset();
+  DecW w;
+  SAMPT_TRY(load_dec(c, &w));
+  DecBufs b;
+  SAMPT_TRY(alloc_dec_bufs(c, &b, w.n_out_tok + K + 2, G * G));
+  int *bbox, *skip; float* box;
+  SAMPT_TRY(ws_get(c, &bbox, 8, "bbox"));
+  SAMPT_TRY(ws_get(c, &skip, 1, "skip"));
+  SAMPT_TRY(ws_get(c, &box, 4, "box"));
+  init_ctl_kernel<<<1, 1, 0, st>>>(bbox, skip, n_refine_done);
+  c->launches++;
+  DecodeCall d{};
+  d.feat_tok = feat_tok; d.n_masks = 1; d.tok0 = 0; d.in_h = in_h; d.in_w = in_w; d.H = H; d.W = W;
+  d.logits = logits; d.iou = iou; d.low_res = low_res; d.skip = nullptr;
+  if (n_pos_first > 0) {
+    d.coords = pos_coords; d.labels = pos_labels; d.K = n_pos_first; d.box = nullptr; d.use_box = 0; d.mask_in = nullptr; d.bbox = nullptr;
+    SAMPT_TRY(decode_once(c, st, w, b, d, G));
+    d.mask_in = low_res;
+  }
+  d.coords = coords; d.labels = labels; d.K = K; d.box = nullptr; d.use_box = 0; d.bbox = bbox;
+  if (n_pos_first <= 0) d.mask_in = nullptr;
+  SAMPT_TRY(decode_once(c, st, w, b, d, G));
+  for (int it = 0; it < n_refine; ++it) {
+    refine_ctl_kernel<<<1, 1, 0, st>>>(bbox, box, skip, n_refine_done);
+    c->launches++;
+    d.box = box; d.use_box = 1; d.mask_in = low_res; d.skip = skip;
+    SAMPT_TRY(decode_once(c, st, w, b, d, G));
+  }
+  SAMPT_LAUNCH_CHECK();
+  return 0;
+}

@@ -8,6 +8,9 @@ namespace sampt {
 int sgemm_nt(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
              const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act);
 
+int sgemm_nt_skip(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
+                  const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip);
+
 // ---- PIPS (pips_kernels.cu)
 struct PipsWin {
   int N, S, stride, frame, T;
@@ -47,4 +50,19 @@ int pips_link(Ctx* c, cudaStream_t st, const PipsWin& w, const float* vis_w, con
 __global__ void conv7x7s2_u8_kernel(const uint8_t* frames, const float* w, const float* bias, float* out, int H, int W,
                                     int Ho, int Wo);
 
+}  // namespace sampt
+
+namespace sampt {
+// ---- SAM ViT helper kernels (vit_kernels.cu)
+int pil_resize(Ctx* c, cudaStream_t st, const uint8_t* in, uint8_t* tmp, uint8_t* out, int B, int H, int W, int Ho, int Wo,
+               const int* hb, const int* hk, int hks, const int* vb, const int* vk, int vks);
+int preprocess_im2col(Ctx* c, cudaStream_t st, const uint8_t* img, __half* A, int B, int Hr, int Wr, int G, int P, int ld,
+                      int split_off, const float* mean, const float* stdv);
+int ln_rows(Ctx* c, cudaStream_t st, const float* x, int ldx, const int* src, const float* gamma, const float* beta, float eps,
+            __half* out, int ldo, int split_off, int Mout, int D, int normalize);
+int attn_prep(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* relh, const float* relw, __half* Qx, __half* Kx,
+              __half* Vt, int nwb, int nheads, int S, int Lkp, int DK, int D, int HD, float scale);
+int neck_ln_im2col(Ctx* c, cudaStream_t st, const float* y1, const float* gamma, const float* beta, __half* A, int B, int G, int C,
+                   int ld, int split_off);
+int neck_ln_nchw(Ctx* c, cudaStream_t st, const float* y2, const float* gamma, const float* beta, float* out, int B, int GG, int C);
 }  // namespace sampt

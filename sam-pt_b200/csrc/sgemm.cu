@@ -12,7 +12,8 @@ template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 sgemm_nt_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw,
                 const float* __restrict__ bias, const float* residual, int ldr, float* Y, int ldy,
-                int M, int N, int K, int act) {
+                int M, int N, int K, int act, const int* skip) {
+  if (skip != nullptr && *skip != 0) return;
   constexpr int NT = (BM / TM) * (BN / TN);
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN + 4];
@@ -124,19 +125,24 @@ sgemm_nt_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ 
 
 int sgemm_nt(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
              const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act) {
+  return sgemm_nt_skip(c, st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, nullptr);
+}
+
+int sgemm_nt_skip(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
+                  const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
   SAMPT_CHECK((K % 4) == 0 && (ldx % 4) == 0 && (ldw % 4) == 0, "sgemm_nt: K/ldx/ldw must be multiples of 4 (K=%d ldx=%d ldw=%d)", K, ldx, ldw);
   if (M <= 0 || N <= 0) return 0;
   // tile choice: big tiles when there is enough work to fill 148 SMs, else smaller tiles for more CTAs
   long long tiles_big = (long long)cdiv(M, 128) * cdiv(N, 64);
   if (tiles_big >= 2 * c->num_sms) {
     dim3 grid(cdiv(N, 64), cdiv(M, 128));
-    sgemm_nt_kernel<128, 64, 16, 8, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act);
+    sgemm_nt_kernel<128, 64, 16, 8, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   } else if ((long long)cdiv(M, 64) * cdiv(N, 64) >= c->num_sms) {
     dim3 grid(cdiv(N, 64), cdiv(M, 64));
-    sgemm_nt_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act);
+    sgemm_nt_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   } else {
     dim3 grid(cdiv(N, 16), cdiv(M, 32));
-    sgemm_nt_kernel<32, 16, 16, 4, 4><<<grid, 32, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act);
+    sgemm_nt_kernel<32, 16, 16, 4, 4><<<grid, 32, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   }
   c->launches++;
   SAMPT_LAUNCH_CHECK();

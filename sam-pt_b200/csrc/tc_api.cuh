@@ -1,0 +1,30 @@
+// Launcher-level API of the tensor-core kernels (gemm_tc.cu, attn_tc.cu), used by the ViT pipeline.
+#pragma once
+#include "common.cuh"
+
+namespace sampt {
+
+struct GemmEpi {
+  // outputs (exactly one of out16 / out32 is used)
+  __half* out16 = nullptr;       // fp16 output [M, ldc]  (bf16 when is_bf16)
+  float* out32 = nullptr;        // fp32 output [rows, ldc]
+  const float* resid = nullptr;  // fp32 residual added to out32 (indexed like out32, or row % resid_mod), may alias out32
+  const float* bias = nullptr;   // [N] or null
+  const int* rowmap = nullptr;   // [M] destination row for out32/resid (-1 = drop the row), or null = identity
+  int ldc = 0;
+  int act = 0;                   // 0 none, 1 GELU(erf)
+  int split_off = 0;             // >0: also write lo = fp16(v - hi) at column offset split_off (out16 only)
+  int is_bf16 = 0;
+  int resid_mod = 0;             // >0: residual row = dest row % resid_mod (broadcast of pos_embed over the frame batch)
+};
+
+// K-loop segments for split precision: segment i multiplies A[:, a_off[i] : a_off[i]+K] with B[:, b_off[i] : b_off[i]+K]
+struct GemmSeg { int nseg; int a_off[3]; int b_off[3]; };
+
+int gemm_tc(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmSeg& seg,
+            const GemmEpi& ep);
+
+int attn_tc(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp,
+            int DK, int HD, int NT, int nheads, __half* out, int ld_out, int split_off);
+
+}  // namespace sampt

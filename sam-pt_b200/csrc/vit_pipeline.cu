@@ -1,0 +1,185 @@
+// Host-side orchestration of SAM's ImageEncoderViT on the B200 (C++; one stream).
+// Upstream: segment_anything/modeling/image_encoder.py (un-vendored); reference call site
+// sam_pt/modeling/sam_pt.py:849 (SamPredictor.set_image).  Frames are batched (B) so every GEMM has M = B*4096 (or
+// B*4900 window-partitioned rows) and fills 148 SMs.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_api.cuh"
+#include "../../include/sampt_b200.h"
+
+namespace sampt {
+
+__global__ void window_map_kernel(int* __restrict__ map, int B, int G, int ws, int nW, long long total) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= total) return;
+  const int L = ws * ws;
+  int t = (int)(r % L);
+  long long wb = r / L;
+  int w = (int)(wb % (nW * nW)), b = (int)(wb / (nW * nW));
+  int y = (w / nW) * ws + t / ws, x = (w % nW) * ws + t % ws;
+  map[r] = (y < G && x < G) ? (b * G * G + y * G + x) : -1;
+}
+
+static GemmSeg make_seg(int precision, int K) {
+  GemmSeg s{};
+  s.nseg = precision;
+  s.a_off[0] = 0; s.b_off[0] = 0;   // hi.hi
+  s.a_off[1] = K; s.b_off[1] = 0;   // lo.hi
+  s.a_off[2] = 0; s.b_off[2] = K;   // hi.lo
+  return s;
+}
+
+struct VitDims { int depth, D, nheads, window, G, P, C; };
+
+static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int Hr, int Wr, const VitDims& d, const int* global_idx,
+                       int n_global, int precision, const float* mean, const float* stdv, float* features, float* interm) {
+  const int D = d.D, G = d.G, GG = G * G, HD = D / d.nheads, ws = d.window;
+  const int nW = (G + ws - 1) / ws, Lw = ws * ws;
+  const int Mtok = B * GG, Mwin = B * nW * nW * Lw;
+  const int asp = precision >= 2 ? 2 : 1;  // A operands carried as hi|lo
+  const int bsp = precision >= 3 ? 2 : 1;  // B operands (weights) carried as hi|lo
+  const int Kpe = 3 * d.P * d.P;
+  const std::string p = "sam.image_encoder.";
+  c->ws_reset();
+
+  float* x;           SAMPT_TRY(ws_get(c, &x, (size_t)Mtok * D, "vit x"));
+  __half* A;          SAMPT_TRY(ws_get(c, &A, (size_t)std::max(Mwin, Mtok) * std::max(D, Kpe) * asp, "vit A"));
+  __half* qkv;        SAMPT_TRY(ws_get(c, &qkv, (size_t)Mwin * 3 * D, "vit qkv"));
+  const int DKw = ((HD + 2 * ws + 63) / 64) * 64, DKg = ((HD + 2 * G + 63) / 64) * 64;
+  const int Lkpw = ((Lw + 63) / 64) * 64;
+  const size_t bh_w = (size_t)B * nW * nW * d.nheads, bh_g = (size_t)B * d.nheads;
+  const size_t q_elems = std::max(bh_w * Lw * DKw, bh_g * GG * DKg);
+  const size_t v_elems = std::max(bh_w * HD * Lkpw, bh_g * HD * GG);
+  __half *Qx, *Kx, *Vt;
+  SAMPT_TRY(ws_get(c, &Qx, q_elems, "vit Qx"));
+  SAMPT_TRY(ws_get(c, &Kx, q_elems, "vit Kx"));
+  SAMPT_TRY(ws_get(c, &Vt, v_elems, "vit Vt"));
+  __half* att;        SAMPT_TRY(ws_get(c, &att, (size_t)Mwin * D * asp, "vit attn out"));
+  __half* hbuf;       SAMPT_TRY(ws_get(c, &hbuf, (size_t)Mtok * std::max(4 * D, 9 * d.C) * asp, "vit mlp hidden"));
+  float* y1;          SAMPT_TRY(ws_get(c, &y1, (size_t)Mtok * d.C * 2, "vit neck y"));
+  int* wmap;          SAMPT_TRY(ws_get(c, &wmap, (size_t)Mwin, "vit window map"));
+  window_map_kernel<<<cdiv(Mwin, 256), 256, 0, st>>>(wmap, B, G, ws, nW, (long long)Mwin);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+
+  // ---- patch embedding (Conv2d k=16 s=16 as a GEMM) + pos_embed
+  {
+    SAMPT_TRY(preprocess_im2col(c, st, img, A, B, Hr, Wr, G, d.P, Kpe * asp, asp == 2 ? Kpe : 0, mean, stdv));
+    const __half* w; const float *bias, *pos;
+    SAMPT_TRY(get_f16(c, p + "patch_embed.w16", &w));
+    SAMPT_TRY(get_f32(c, p + "patch_embed.proj.bias", &bias));
+    SAMPT_TRY(get_f32(c, p + "pos_embed", &pos));
+    GemmEpi ep{};
+    ep.out32 = x; ep.resid = pos; ep.resid_mod = GG; ep.bias = bias; ep.ldc = D;
+    SAMPT_TRY(gemm_tc(c, st, A, Kpe * asp, w, Kpe * bsp, Mtok, D, Kpe, make_seg(precision, Kpe), ep));
+  }
+
+  int gi = 0;
+  for (int blk = 0; blk < d.depth; ++blk) {
+    bool is_global = false;
+    for (int i = 0; i < n_global; ++i) is_global |= (global_idx[i] == blk);
+    const std::string bp = p + "blocks." + std::to_string(blk) + ".";
+    const float *n1w, *n1b, *n2w, *n2b, *qkvb, *projb, *l1b, *l2b, *rph, *rpw;
+    const __half *wqkv, *wproj, *wl1, *wl2;
+    SAMPT_TRY(get_f32(c, bp + "norm1.weight", &n1w)); SAMPT_TRY(get_f32(c, bp + "norm1.bias", &n1b));
+    SAMPT_TRY(get_f32(c, bp + "norm2.weight", &n2w)); SAMPT_TRY(get_f32(c, bp + "norm2.bias", &n2b));
+    SAMPT_TRY(get_f32(c, bp + "attn.qkv.bias", &qkvb)); SAMPT_TRY(get_f32(c, bp + "attn.proj.bias", &projb));
+    SAMPT_TRY(get_f32(c, bp + "mlp.lin1.bias", &l1b)); SAMPT_TRY(get_f32(c, bp + "mlp.lin2.bias", &l2b));
+    SAMPT_TRY(get_f32(c, bp + "attn.rel_pos_h", &rph)); SAMPT_TRY(get_f32(c, bp + "attn.rel_pos_w", &rpw));
+    SAMPT_TRY(get_f16(c, bp + "attn.qkv.w16", &wqkv)); SAMPT_TRY(get_f16(c, bp + "attn.proj.w16", &wproj));
+    SAMPT_TRY(get_f16(c, bp + "mlp.lin1.w16", &wl1)); SAMPT_TRY(get_f16(c, bp + "mlp.lin2.w16", &wl2));
+
+    const int Mrows = is_global ? Mtok : Mwin;
+    const int S = is_global ? G : ws;
+    const int L = S * S;
+    const int nwb = is_global ? B : B * nW * nW;
+    const int DK = is_global ? DKg : DKw;
+    const int Lkp = is_global ? GG : Lkpw;
+    const int NT = is_global ? 128 : (((Lw + 15) / 16) * 16 <= 256 ? ((Lw + 15) / 16) * 16 : 128);
+    // LN1 (+ window partition with zero padding)
+    SAMPT_TRY(ln_rows(c, st, x, D, is_global ? nullptr : wmap, n1w, n1b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mrows, D, 1));
+    // qkv = Linear(D, 3D)
+    {
+      GemmEpi ep{};
+      ep.out16 = qkv; ep.bias = qkvb; ep.ldc = 3 * D;
+      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wqkv, D * bsp, Mrows, 3 * D, D, make_seg(precision, D), ep));
+    }
+    // attention
+    SAMPT_TRY(attn_prep(c, st, qkv, 3 * D, rph, rpw, Qx, Kx, Vt, nwb, d.nheads, S, Lkp, DK, D, HD, 1.0f / sqrtf((float)HD)));
+    SAMPT_TRY(attn_tc(c, st, Qx, Kx, Vt, nwb * d.nheads, L, L, Lkp, DK, HD, NT, d.nheads, att, D * asp, asp == 2 ? D : 0));
+    // x = x + proj(attn)   (window un-partition via the row map; padding rows are dropped)
+    {
+      GemmEpi ep{};
+      ep.out32 = x; ep.resid = x; ep.bias = projb; ep.ldc = D; ep.rowmap = is_global ? nullptr : wmap;
+      SAMPT_TRY(gemm_tc(c, st, att, D * asp, wproj, D * bsp, Mrows, D, D, make_seg(precision, D), ep));
+    }
+    // x = x + lin2(gelu(lin1(LN2(x))))
+    SAMPT_TRY(ln_rows(c, st, x, D, nullptr, n2w, n2b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mtok, D, 1));
+    {
+      GemmEpi ep{};
+      ep.out16 = hbuf; ep.bias = l1b; ep.ldc = 4 * D * asp; ep.act = 1; ep.split_off = asp == 2 ? 4 * D : 0;
+      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wl1, D * bsp, Mtok, 4 * D, D, make_seg(precision, D), ep));
+    }
+    {
+      GemmEpi ep{};
+      ep.out32 = x; ep.resid = x; ep.bias = l2b; ep.ldc = D;
+      SAMPT_TRY(gemm_tc(c, st, hbuf, 4 * D * asp, wl2, 4 * D * bsp, Mtok, D, 4 * D, make_seg(precision, 4 * D), ep));
+    }
+    if (is_global) {
+      if (interm && gi == 0)
+        SAMPT_CUDA(cudaMemcpyAsync(interm, x, (size_t)Mtok * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      ++gi;
+    }
+  }
+
+  // ---- neck: conv1x1 (no bias) -> LayerNorm2d -> conv3x3 (no bias) -> LayerNorm2d
+  {
+    const int C = d.C;
+    const __half *w0, *w2;
+    const float *g1, *b1, *g3, *b3;
+    SAMPT_TRY(get_f16(c, p + "neck.0.w16", &w0)); SAMPT_TRY(get_f16(c, p + "neck.2.w16", &w2));
+    SAMPT_TRY(get_f32(c, p + "neck.1.weight", &g1)); SAMPT_TRY(get_f32(c, p + "neck.1.bias", &b1));
+    SAMPT_TRY(get_f32(c, p + "neck.3.weight", &g3)); SAMPT_TRY(get_f32(c, p + "neck.3.bias", &b3));
+    SAMPT_TRY(ln_rows(c, st, x, D, nullptr, nullptr, nullptr, 0.f, A, D * asp, asp == 2 ? D : 0, Mtok, D, 0));  // cast only
+    float* y2 = y1 + (size_t)Mtok * C;
+    {
+      GemmEpi ep{};
+      ep.out32 = y1; ep.ldc = C;
+      SAMPT_TRY(gemm_tc(c, st, A, D * asp, w0, D * bsp, Mtok, C, D, make_seg(precision, D), ep));
+    }
+    __half* A2 = hbuf;  // Mtok * 9C * asp halves
+    SAMPT_TRY(neck_ln_im2col(c, st, y1, g1, b1, A2, B, G, C, 9 * C * asp, asp == 2 ? 9 * C : 0));
+    {
+      GemmEpi ep{};
+      ep.out32 = y2; ep.ldc = C;
+      SAMPT_TRY(gemm_tc(c, st, A2, 9 * C * asp, w2, 9 * C * bsp, Mtok, C, 9 * C, make_seg(precision, 9 * C), ep));
+    }
+    SAMPT_TRY(neck_ln_nchw(c, st, y2, g3, b3, features, B, GG, C));
+  }
+  return 0;
+}
+
+}  // namespace sampt
+
+using namespace sampt;
+
+extern "C" int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B, int Hr, int Wr, int depth, int embed_dim,
+                                int num_heads, int window_size, const int* global_idx_host, int n_global, int img_size,
+                                int patch_size, int out_chans, int precision, const float* pixel_mean_host,
+                                const float* pixel_std_host, float* features, float* interm, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  SAMPT_CHECK(precision >= 1 && precision <= 3, "sampt_vit_encode: precision must be 1..3");
+  SAMPT_CHECK(img_size % patch_size == 0, "img_size must be a multiple of patch_size");
+  SAMPT_CHECK(Hr <= img_size && Wr <= img_size, "resized image (%dx%d) exceeds img_size %d", Hr, Wr, img_size);
+  SAMPT_CHECK(embed_dim % 128 == 0 && embed_dim % num_heads == 0, "embed_dim must be a multiple of 128 and of num_heads");
+  VitDims d{depth, embed_dim, num_heads, window_size, img_size / patch_size, patch_size, out_chans};
+  return vit_forward(c, reinterpret_cast<cudaStream_t>(stream), resized_u8, B, Hr, Wr, d, global_idx_host, n_global, precision,
+                     pixel_mean_host, pixel_std_host, features, interm);
+}
+
+extern "C" int sampt_pil_resize_u8(sampt_ctx* ctx, const uint8_t* in, int B, int H, int W, int Ho, int Wo, const int* hbounds,
+                                   const int* hcoef, int hksize, const int* vbounds, const int* vcoef, int vksize, uint8_t* tmp,
+                                   uint8_t* out, void* stream) {
+  return pil_resize(reinterpret_cast<Ctx*>(ctx), reinterpret_cast<cudaStream_t>(stream), in, tmp, out, B, H, W, Ho, Wo, hbounds,
+                    hcoef, hksize, vbounds, vcoef, vksize);
+}
