@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- SAM-PT hot path throughput on B200 (contract: see the task brief / DESIGN.md §measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C1|...]
+
+A "step" = one pass of the hot path (PIPS track -> SAM ViT encode -> prompt+mask decode with 12 refinements) over one
+synthetic clip.  Headline workload = BASELINE config C2: 50 frames 480x854, SAM ViT-H + PIPS, 1 mask x 8 positive points.
+`value`  : frames/s with the uint8 clip already resident in HBM (CUDA events, max over ranks).
+`e2e`    : frames/s through the public API `SamPt.forward(video)` with the clip in pinned HOST memory (H2D inside the timed
+           region) and the result summary (scores + trajectories + visibilities) read back D2H.
+`--impl reference`: the reference's own CPU path (oracle port: reference PIPS restated + SAM restated, torch CPU, all host
+           threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "sam-pt_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: (T, H, W, vit, P)
+    "C1": (2, 240, 320, "vit_b", 4),
+    "C2": (50, 480, 854, "vit_h", 8),
+    "C2b": (50, 480, 854, "vit_b", 8),
+}
+SAM_SEED, PIPS_SEED = 7202, 7201
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=3)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_weights(vit):
+    """Seeded synthetic checkpoints, shapes taken from the product modules themselves (same tables as the oracle's)."""
+    from sampt_b200 import factory, synth
+    from sam_pt.point_tracker.pips.pips import _pips_shapes
+    sam = factory.build_sam(vit)
+    shapes = {k: tuple(v.shape) for k, v in sam.state_dict().items()}
+    sam_sd = synth.condition_sam(synth.make_state_dict(shapes, SAM_SEED))
+    pips_sd = synth.condition_pips(synth.make_state_dict(_pips_shapes(8), PIPS_SEED))
+    return sam_sd, pips_sd
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from sampt_b200 import factory, synth, native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, H, W, vit, P = CONFIGS[args.config]
+    sam_sd, pips_sd = make_weights(vit)
+    tmp = tempfile.mkdtemp(prefix="sampt_bench_")
+    ckpt = synth.write_pips_checkpoint_dir(pips_sd, os.path.join(tmp, "pips"))
+    model = factory.build_sam_pt(vit, sam_sd, ckpt, positive_points_per_mask=P, sam_iou_threshold=-1e9, device=dev)
+    model.sam_predictor.model.image_encoder.precision = args.precision
+    model.encoder_batch = args.encoder_batch
+    # weak scaling: every rank processes its own clip (seed 72 + rank): clips shard with no data-path collective
+    video = synth.make_video_dict(T, H, W, P, seed=72 + rank)
+    frames_host = torch.stack(video["image"]).pin_memory()
+    q_host = video["query_points"].pin_memory()
+    ctx = native.get_context(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB): flushed between timed iterations
+
+    def step_resident(frames_dev, q_dev):
+        traj, vis, logits, scores, spf = model._forward(frames_dev, q_dev)
+        return logits, spf, traj, vis
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up
+    frames_dev = frames_host.to(dev)
+    q_dev = q_host.to(dev)
+    for _ in range(max(args.warmup, 1)):
+        step_resident(frames_dev, q_dev)
+    torch.cuda.synchronize()
+
+    # ---------------- timed: resident inputs
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clk:
+        barrier()
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            step_resident(frames_dev, q_dev)
+            ev[i][1].record()
+        barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = ctx.launch_count() - launches0
+    # ---------------- timed: end to end through SamPt.forward with HOST inputs + D2H result summary
+    video_host = dict(video)
+    video_host["image"] = [f for f in frames_host]
+    video_host["query_points"] = q_host
+    model(video_host)  # warm
+    torch.cuda.synchronize()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    d2h = 0
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)
+        ev2[i][0].record()
+        out = model(video_host)
+        summary = (out["trajectories"].cpu(), out["visibilities"].cpu(), torch.stack([l.amax(dim=(1, 2)) for l in out["logits"]]).cpu())
+        ev2[i][1].record()
+        d2h = sum(t.numel() * t.element_size() for t in summary) + 8 * (len(out["scores"]) + T)
+    barrier()
+    ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    # ---------------- roofline of the dominant kernel (ViT tcgen05 GEMM), measured live with CUDA events
+    roof = gemm_roofline(model, dev, args)
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline(args.config, sample_frames=args.cpu_sample_frames)
+    if rank == 0:
+        frames_total = T * world * args.steps
+        line = {
+            "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
+            "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 hi+lo activations (fp32 accumulate)", 3: "f16 hi+lo split x3 (~fp32)"}[args.precision]
+                     + " ViT; f32 PIPS + decoder",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS (S=8, stride 4), 1 mask x {P} points, "
+                                   f"12 refinement iterations, random-init conditioned weights",
+                       "clips_per_step": world, "parallelism": f"clip-per-GPU x{world}" if world > 1 else "single GPU",
+                       "l2": "flushed between timed iterations (256 MiB write)", "vit_precision_passes": args.precision,
+                       "encoder_batch": args.encoder_batch},
+            "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(frames_host.numel() + q_host.numel() * 4), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": roof,
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gemm_roofline(model, dev, args):
+    """Times the ViT's largest GEMM shape (mlp.lin1: M=B*4096, N=4D, K=D) in isolation with CUDA events."""
+    from ctypes import c_int
+    from sampt_b200 import native
+    enc = model.sam_predictor.model.image_encoder
+    D, B = enc.embed_dim, args.encoder_batch
+    M, N, K = B * 4096, 4 * D, D
+    p = args.precision
+    asp, bsp = (2 if p >= 2 else 1), (2 if p >= 3 else 1)
+    A = torch.randn((M, K * asp), device=dev).half()
+    Wt = torch.randn((N, K * bsp), device=dev).half()
+    out = torch.empty((M, N), device=dev, dtype=torch.float16)
+    ctx = native.get_context(dev)
+    L = native.lib()
+
+    def run():
+        native.check(L.sampt_gemm_f16(ctx.handle, native.ptr(A), c_int(K * asp), native.ptr(Wt), c_int(K * bsp), c_int(M), c_int(N),
+                                      c_int(K), c_int(p), c_int(0), native.ptr(None), c_int(0), native.ptr(out), native.ptr(None),
+                                      native.ptr(None), c_int(N), c_int(0), native.stream_ptr()))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops_alg = 2.0 * M * N * K           # algorithmic (what the layer needs)
+    flops_exec = flops_alg * p            # tensor-core work actually issued (split passes)
+    pk = _peaks()
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel (ViT mlp.lin1 shape)", "achieved": flops_exec / (ms * 1e-3) / 1e12,
+            "achieved_algorithmic": flops_alg / (ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": flops_exec / (ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["src"] + ", burst",
+            "shape": [M, N, K], "passes": p, "ms": ms}
+
+
+def cpu_baseline(config, sample_frames=2):
+    """Reference CPU path (oracle port) on a bounded sample of the workload: `sample_frames` frames of the same clip."""
+    from oracle import pips_ref, sam_ref, sampt_ref
+    from sampt_b200 import synth
+    T, H, W, vit, P = CONFIGS[config]
+    cfg = {"vit_b": sam_ref.VIT_B, "vit_h": sam_ref.VIT_H, "vit_l": sam_ref.VIT_L}[vit]
+    torch.set_num_threads(os.cpu_count())
+    sam_sd = synth.condition_sam(synth.make_state_dict(sam_ref.sam_state_dict_shapes(cfg), SAM_SEED))
+    pips_sd = synth.condition_pips(synth.make_state_dict(pips_ref.pips_state_dict_shapes(), PIPS_SEED))
+    n = min(sample_frames, T)
+    video = synth.make_video_dict(T, H, W, P)
+    video["image"] = video["image"][:n]
+    t0 = time.time()
+    sampt_ref.sampt_forward(pips_sd, sam_ref.RefSamPredictor(sam_sd, cfg), video, positive_points_per_mask=P, sam_iou_threshold=-1e9)
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"first {n} of {T} frames of the {config} clip (tracker + ViT + decode with 12 refinements), {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T, H, W, vit, P = CONFIGS[args.config]
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 2))):
+        base = cpu_baseline(args.config, sample_frames=args.cpu_sample_frames)
+        vals.append(base["value"])
+    v = sum(vals) / len(vals)
+    base["value"] = v
+    line = {"impl": "reference", "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
+            "value": v, "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * T / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS, 1 mask x {P} points (bounded sample: "
+                                   f"{base['sample']})"},
+            "cpu_baseline": base, "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("SAMPT_VIT_PRECISION", "3")))
+    ap.add_argument("--encoder-batch", type=int, default=10)
+    ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

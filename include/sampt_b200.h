@@ -80,6 +80,41 @@ int sampt_gemm_f16(sampt_ctx* ctx, const void* A, int lda, const void* B, int ld
                    int is_bf16, const float* bias, int act, void* out16, float* out32, const float* resid, int ldc,
                    int split_off, void* stream);
 
+/* softmax(Qx Kx^T) V on tcgen05 with pre-extended operands (rel-pos folded into the contraction, see csrc/attn_tc.cu):
+ * Qx [BH,Lq,DK], Kx [BH,Lk,DK], Vt [BH,HD,Lkp] fp16; out fp16 [(BH/nheads)*Lq, ld_out] with head h at columns h*HD.
+ * Replaces Attention.forward + add_decomposed_rel_pos of upstream image_encoder.py. */
+int sampt_attention_f16(sampt_ctx* ctx, const void* Qx, const void* Kx, const void* Vt, int BH, int Lq, int Lk, int Lkp, int DK,
+                        int HD, int NT, int nheads, void* out, int ld_out, int split_off, void* stream);
+
+/* ---- SAM image encoder ------------------------------------------------------------------------------------------ */
+/* ResizeLongestSide.apply_image (PIL bilinear, bit-exact): planar uint8 (B,3,H,W) -> (B,3,Ho,Wo); coefficient tables
+ * (device int32) come from sampt_b200/pil_resize.py; tmp is a (B,3,H,Wo) uint8 scratch. */
+int sampt_pil_resize_u8(sampt_ctx* ctx, const uint8_t* in, int B, int H, int W, int Ho, int Wo, const int* hbounds,
+                        const int* hcoef, int hksize, const int* vbounds, const int* vcoef, int vksize, uint8_t* tmp,
+                        uint8_t* out, void* stream);
+/* Sam.preprocess + ImageEncoderViT.forward for a batch of resized uint8 frames (B,3,Hr,Wr) -> features (B,C,g,g) fp32
+ * [+ interm (B,g,g,D): output of the first global-attention block, HQ-SAM].  global_idx / pixel_mean / pixel_std are
+ * HOST arrays.  precision: see sampt_gemm_f16.  Replaces SamPredictor.set_image's encoder call (sam_pt.py:849). */
+int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B, int Hr, int Wr, int depth, int embed_dim, int num_heads,
+                     int window_size, const int* global_idx_host, int n_global, int img_size, int patch_size, int out_chans,
+                     int precision, const float* pixel_mean_host, const float* pixel_std_host, float* features, float* interm,
+                     void* stream);
+
+/* ---- SAM prompt encoder + mask decoder + postprocess ------------------------------------------------------------- */
+/* (C, g*g) NCHW feature map -> token-major (g*g, C) */
+int sampt_sam_features_to_tokens(sampt_ctx* ctx, const float* feat_nchw, float* feat_tok, int C, int GG, void* stream);
+/* SamPredictor.predict_torch for one prompt set: coords (K,2) in the 1024 frame, labels (K) int32, box (4) or NULL,
+ * mask_input (256*256) or NULL; multimask 0 -> 1 mask (token 0), 1 -> 3 masks (tokens 1..3).
+ * logits (n,H,W), iou (n), low_res (n,256,256).  Reference call sites sam_pt/modeling/sam_pt.py:783-828. */
+int sampt_sam_predict(sampt_ctx* ctx, const float* feat_tok, int G, const float* coords, const int* labels, int K,
+                      const float* box, const float* mask_input, int multimask, int in_h, int in_w, int H, int W, float* logits,
+                      float* iou, float* low_res, void* stream);
+/* SamPt.predict_mask (sam_pt.py:760-837) fused: [positive-only call +] full call + n_refine box/mask refinements with the
+ * `mask area < 2` break evaluated on the device (no host synchronisation).  n_refine_done: device int32 [1]. */
+int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const float* coords, const int* labels, int K,
+                             const float* pos_coords, const int* pos_labels, int n_pos_first, int n_refine, int in_h, int in_w,
+                             int H, int W, float* logits, float* iou, float* low_res, int* n_refine_done, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
