@@ -1,0 +1,52 @@
+"""CPU, world_size 2 over gloo: the frame-sharding index arithmetic and the all-gather wrapper used on the multi-GPU path."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, T, ret):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "sam-pt_b200"))
+    from sampt_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(T * 3 * 2, dtype=torch.float32).reshape(T, 3, 2)  # "feature maps": frame f -> distinct values
+    mine = full[sharding.owned_frames(T, rank, world)]
+    got = sharding.allgather_frames(mine, T)
+    ok = torch.equal(got, full) and torch.equal(sharding.scatter_rows_by_frame(got, rank, world), mine)
+    t = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    # max-over-ranks timing reduction used by bench.py
+    ms = torch.tensor([10.0 + rank], dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ret.put((float(t.item()), float(ms.item())))
+    dist.destroy_process_group()
+
+
+def test_allgather_frames_world2():
+    for T in (50, 7):  # divisible and ragged
+        ctx = mp.get_context("spawn")
+        ret = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, T, ret)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+        ok, ms = ret.get(timeout=10)
+        assert ok == 1.0 and ms == 11.0
