@@ -123,7 +123,9 @@ def run_ours(args):
     model = factory.build_sam_pt(vit, sam_sd, ckpt, positive_points_per_mask=P, sam_iou_threshold=-1e9, device=dev)
     model.sam_predictor.model.image_encoder.precision = args.precision
     model.encoder_batch = args.encoder_batch
-    # weak scaling: every rank processes its own clip (seed 72 + rank): clips shard with no data-path collective
+    if world > 1 and args.mgpu_mode == "frame_shard":
+        return run_ours_frame_sharded(args, model, dev, rank, world, local)
+    # clip-per-GPU: every rank processes its own clip (seed 72 + rank), no data-path collective
     video = synth.make_video_dict(T, H, W, P, seed=72 + rank)
     frames_host = torch.stack(video["image"]).pin_memory()
     q_host = video["query_points"].pin_memory()
@@ -182,6 +184,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    breakdown = stage_breakdown(model, frames_dev, q_dev) if args.breakdown else None
     # ---------------- roofline of the dominant kernel (ViT tcgen05 GEMM), measured live with CUDA events
     roof = gemm_roofline(model, dev, args)
     cpu_base = None
@@ -208,9 +211,120 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu_base,
         }
+        if breakdown:
+            line["breakdown_ms"] = breakdown
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_ours_frame_sharded(args, model, dev, rank, world, local):
+    """N > 1, BASELINE config C4 shape: `world` clips per step, frames of every clip sharded round-robin over the ranks,
+    one NCCL all-gather of the PIPS feature maps (SamPt.forward_clips_sharded).  Weak scaling: clips/step == ranks."""
+    import torch.distributed as dist
+    from sampt_b200 import native, synth
+    T, H, W, vit, P = CONFIGS[args.config]
+    videos = [synth.make_video_dict(T, H, W, P, seed=72 + c) for c in range(world)]
+    host = [dict(v, image=[f.pin_memory() for f in v["image"]]) for v in videos]
+    resident = [dict(v, image=[f.to(dev) for f in v["image"]], query_points=v["query_points"].to(dev)) for v in videos]
+    ctx = native.get_context(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        model.forward_clips_sharded(resident)
+    torch.cuda.synchronize()
+
+    def timed(inputs, readback):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        nbytes = 0
+        barrier()
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            res = model.forward_clips_sharded(inputs)
+            if readback:
+                summ = [(r["trajectories"].cpu(), r["visibilities"].cpu(), r["scores_per_frame"].cpu(),
+                         r["logits"].amax(dim=(2, 3)).cpu()) for r in res]
+                nbytes = sum(t.numel() * t.element_size() for tup in summ for t in tup)
+            ev[i][1].record()
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in ev), nbytes
+
+    l0 = ctx.launch_count()
+    with ClockSampler(local) as clk:
+        ms, _ = timed(resident, False)
+    launches = ctx.launch_count() - l0
+    model.forward_clips_sharded(host)
+    ms_e2e, d2h = timed(host, True)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    roof = gemm_roofline(model, dev, args)
+    if rank == 0:
+        frames_total = T * world * args.steps
+        own = len(range(rank, T, world))
+        line = {
+            "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
+            "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 hi+lo activations (fp32 accumulate)", 3: "f16 hi+lo split x3 (~fp32)"}[args.precision]
+                     + " ViT; f32 PIPS + decoder",
+            "data": "synthetic",
+            "config": {"workload": f"{world} x {args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS, 1 mask x {P} points, 12 refinements; "
+                                   f"frames sharded round-robin over {world} GPUs, one NCCL all-gather of fp32 PIPS feature maps",
+                       "clips_per_step": world, "parallelism": f"frame-shard x{world} + all-gather",
+                       "l2": "flushed between timed iterations (256 MiB write)", "vit_precision_passes": args.precision,
+                       "encoder_batch": args.encoder_batch},
+            "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": "frames/s",
+                    "h2d_bytes_per_step": int(world * own * 3 * H * W + world * P * 12), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+def stage_breakdown(model, frames_dev, q_dev):
+    """Per-stage device time of one step (CUDA events; separate untimed pass, for DESIGN/PROFILE notes only)."""
+    pred = model.sam_predictor
+    trk = model.point_tracker
+    T = frames_dev.shape[0]
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return r, a.elapsed_time(b)
+
+    out = {}
+    pyr, out["pips_fnet_pyramid"] = timed(lambda: trk.model.encode_frames(frames_dev))
+    q = q_dev.reshape(-1, 3).float().to(frames_dev.device)
+    _, out["pips_chain"] = timed(lambda: trk.model.track(pyr, q, 0.9, iters=6, flip=False))
+    B = model.encoder_batch
+    t_res = t_vit = 0.0
+    feats = None
+    for f0 in range(0, T, B):
+        r, ms = timed(lambda: pred.resize_frames_u8(frames_dev[f0:f0 + B]))
+        t_res += ms
+        m = pred.model
+        feats, ms = timed(lambda: m.image_encoder.encode_resized_u8(r, m.pixel_mean.flatten().tolist(), m.pixel_std.flatten().tolist()))
+        t_vit += ms
+    out["sam_resize"], out["sam_vit_encode"] = t_res, t_vit
+    pred.set_frames_features(tuple(frames_dev.shape[-2:]), feats[:1])
+    c = torch.rand((q.shape[0], 2), device=frames_dev.device) * 500
+    lab = torch.ones((q.shape[0],), dtype=torch.int32, device=frames_dev.device)
+    lg = torch.empty(tuple(frames_dev.shape[-2:]), device=frames_dev.device)
+    pred.predict_refine(c, lab, 0, 12, lg)
+    _, ms = timed(lambda: [pred.predict_refine(c, lab, 0, 12, lg) for _ in range(5)])
+    out["sam_decode_13calls_per_frame"] = ms / 5
+    out["sam_decode_clip_estimate"] = ms / 5 * T
+    return {k: round(v, 3) for k, v in out.items()}
 
 
 def gemm_roofline(model, dev, args):
@@ -303,6 +417,8 @@ def main():
     ap.add_argument("--encoder-batch", type=int, default=10)
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true")
+    ap.add_argument("--mgpu-mode", default="frame_shard", choices=["frame_shard", "clip_per_gpu"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -37,6 +37,10 @@ int sampt_ctx_create(int device, sampt_ctx** out);
 int sampt_ctx_destroy(sampt_ctx* ctx);
 /* caller-owned scratch slab that pipelines bump-allocate from (no cudaMalloc inside the library) */
 int sampt_ctx_set_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes);
+/* optional second slab with STABLE addresses for the SAM decode chain: when set, sampt_sam_predict_refine captures one CUDA
+ * graph per chain shape and replays it (one launch per frame instead of ~500).  Re-setting it drops the cached graphs
+ * (must be called after decoder weights are re-registered). */
+int sampt_ctx_set_decoder_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes);
 /* register a caller-owned device tensor under a name (weights in kernel-native layout; replaces the
  * load_state_dict contract of sam_pt/modeling/sam.py:18-31 and sam_pt/point_tracker/utils/saverloader.py:30-73) */
 int sampt_set_tensor(sampt_ctx* ctx, const char* name, void* dev_ptr, int dtype, int ndim, const int64_t* dims);

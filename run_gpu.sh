@@ -1,8 +1,7 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-timeout -s KILL 400 python -m pytest tests/test_gpu_gemm.py -q -m gpu --timeout 120 2>&1 | tail -40 > gpurun_out/t_gemm.log
-timeout -s KILL 400 python -m pytest tests/test_gpu_attention.py -q -m gpu --timeout 120 2>&1 | tail -40 > gpurun_out/t_attn.log
-timeout -s KILL 900 python -m pytest tests/test_gpu_sam.py -q -m gpu --timeout 300 2>&1 | tail -80 > gpurun_out/t_sam.log
-timeout -s KILL 300 python bench.py --config C1 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_c1.log 2>&1
-timeout -s KILL 600 python bench.py --config C2 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_c2.log 2>&1
-tail -5 gpurun_out/t_gemm.log gpurun_out/t_attn.log gpurun_out/t_sam.log gpurun_out/bench_c1.log gpurun_out/bench_c2.log
+timeout -s KILL 900 python bench.py --config C2 --steps 2 --warmup 1 --no-cpu-baseline --breakdown > gpurun_out/bench_c2_p3.log 2>&1
+timeout -s KILL 600 python bench.py --config C2 --steps 2 --warmup 1 --no-cpu-baseline --precision 1 > gpurun_out/bench_c2_p1.log 2>&1
+timeout -s KILL 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 70000 --csv --log-file gpurun_out/launches_c2.csv python bench.py --config C2 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 40 -c 2 -o gpurun_out/prof_gemm python bench.py --config C2b --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
+for f in gpurun_out/bench_c2_p3.log gpurun_out/bench_c2_p1.log; do tail -n 1 $f; done
+ls -la gpurun_out

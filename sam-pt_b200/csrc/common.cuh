@@ -10,6 +10,7 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <map>
 
 namespace sampt {
 
@@ -67,6 +68,11 @@ struct Ctx {
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   long long launches = 0;  // kernels launched through this ctx (bench.py reports it as gpu_launches)
+  // decoder slab + captured CUDA graphs of the SAM refinement chain (decoder.cu)
+  char* dec_base = nullptr;
+  size_t dec_bytes = 0, dec_off = 0;
+  cudaStream_t cap_stream = nullptr;
+  std::map<std::vector<int>, void*> graph_cache;
 
   const TensorRef* find(const std::string& name) const {
     auto it = tensors.find(name);

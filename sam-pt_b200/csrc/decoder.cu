@@ -253,6 +253,88 @@ attn_q_small_kernel(const float* __restrict__ q, const float* __restrict__ k, co
   }
 }
 
+// tokens -> image attention, split over the keys (flash-decoding style): grid (S splits, H heads).  Each block stages its
+// slice of K/V (keys_per_split x DH, read exactly once, coalesced) in shared memory; warp w serves tokens w, w+8, ...;
+// lanes stride over the slice's keys.  Partial (max, sum, acc[DH]) per (token, head, split) -> combine kernel.
+template <int DH, int KPS>
+__global__ void __launch_bounds__(256)
+attn_t2i_partial_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                        float* __restrict__ part, int T, int Nk, int H, const int* skip) {
+  SKIP_RETURN(skip);
+  __shared__ float sk[KPS][DH + 1];
+  __shared__ float sv[KPS][DH + 1];
+  const int split = blockIdx.x, h = blockIdx.y, nsplit = gridDim.x;
+  const int ld = H * DH;
+  const int j0 = split * KPS;
+  for (int i = threadIdx.x; i < KPS * DH; i += 256) {
+    int j = i / DH, d = i % DH;
+    float kv = 0.f, vv = 0.f;
+    if (j0 + j < Nk) { kv = k[(size_t)(j0 + j) * ld + h * DH + d]; vv = v[(size_t)(j0 + j) * ld + h * DH + d]; }
+    sk[j][d] = kv; sv[j][d] = vv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float scale = 1.0f / sqrtf((float)DH);
+  const int nvalid = min(KPS, Nk - j0);
+  for (int t = warp; t < T; t += 8) {
+    float qv[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) qv[d] = q[(size_t)t * ld + h * DH + d];
+    float sc[KPS / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < KPS / 32; ++i) {
+      int j = lane + 32 * i;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) s = fmaf(qv[d], sk[j][d], s);
+      s *= scale;
+      sc[i] = (j < nvalid) ? s : -INFINITY;
+      mx = fmaxf(mx, sc[i]);
+    }
+    mx = warp_max(mx);
+    float acc[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+    float lsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPS / 32; ++i) {
+      int j = lane + 32 * i;
+      float p = (j < nvalid) ? expf(sc[i] - mx) : 0.f;
+      lsum += p;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, sv[j][d], acc[d]);
+    }
+    lsum = warp_sum(lsum);
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = warp_sum(acc[d]);
+    if (lane == 0) {
+      float* o = part + (((size_t)t * H + h) * nsplit + split) * (DH + 2);
+      o[0] = mx; o[1] = lsum;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) o[2 + d] = acc[d];
+    }
+  }
+}
+template <int DH>
+__global__ void attn_t2i_combine_kernel(const float* __restrict__ part, float* __restrict__ out, int T, int H, int nsplit,
+                                        const int* skip) {
+  SKIP_RETURN(skip);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (t, h, d)
+  if (idx >= T * H * DH) return;
+  const int d = idx % DH, h = (idx / DH) % H, t = idx / (DH * H);
+  const float* p = part + ((size_t)t * H + h) * nsplit * (DH + 2);
+  float mx = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) mx = fmaxf(mx, p[s * (DH + 2)]);
+  float l = 0.f, a = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    float w = expf(p[s * (DH + 2)] - mx);
+    l += w * p[s * (DH + 2) + 1];
+    a += w * p[s * (DH + 2) + 2 + d];
+  }
+  out[(size_t)t * H * DH + h * DH + d] = a / l;
+}
+
 // image tokens attend to the (few) prompt tokens: q [N, H*DH], k/v [T, H*DH], T <= 512.  One thread per (image token, head).
 template <int DH>
 __global__ void __launch_bounds__(256)
@@ -546,7 +628,7 @@ static int load_dec(Ctx* c, DecW* w) {
 struct DecBufs {
   float *tokens, *queries, *qpe, *tq, *tk, *tv, *ta, *tmp, *mlp_h;   // token side  (T rows)
   float *src, *keys, *ik, *iv, *iq, *ia;                            // image side  (4096 rows)
-  float *u1, *hyper, *iou4;
+  float *u1, *hyper, *iou4, *part;
   int T;
 };
 
@@ -564,8 +646,14 @@ static int attn_tok_to_img(Ctx* c, cudaStream_t st, const AttnW& a, const float*
   SAMPT_TRY(sg(c, st, q_in, 256, a.qw, a.qb, nullptr, 0, b.tq, 128, T, 128, 256, 0, skip));
   SAMPT_TRY(sg(c, st, keys, 256, a.kw, a.kb, pek, 128, b.ik, 128, GG, 128, 256, 0, skip));   // (keys + key_pe) Wk^T
   SAMPT_TRY(sg(c, st, keys, 256, a.vw, a.vb, nullptr, 0, b.iv, 128, GG, 128, 256, 0, skip));
-  attn_q_small_kernel<16><<<dim3(T, 8), 256, 0, st>>>(b.tq, b.ik, b.iv, b.ta, GG, 8, skip);
-  LAUNCH_OK();
+  {
+    constexpr int KPS = 256;
+    const int nsplit = (GG + KPS - 1) / KPS;
+    attn_t2i_partial_kernel<16, KPS><<<dim3(nsplit, 8), 256, 0, st>>>(b.tq, b.ik, b.iv, b.part, T, GG, 8, skip);
+    LAUNCH_OK();
+    attn_t2i_combine_kernel<16><<<cdiv(T * 128, 128), 128, 0, st>>>(b.part, b.ta, T, 8, nsplit, skip);
+    LAUNCH_OK();
+  }
   SAMPT_TRY(sg(c, st, b.ta, 128, a.ow, a.ob, resid, 256, out, 256, T, 256, 128, 0, skip));
   return 0;
 }
@@ -699,6 +787,7 @@ static int alloc_dec_bufs(Ctx* c, DecBufs* b, int Tmax, int GG) {
   SAMPT_TRY(ws_get(c, &b->u1, (size_t)GG * 256, "dec u1"));
   SAMPT_TRY(ws_get(c, &b->hyper, (size_t)4 * 32, "dec hyper"));
   SAMPT_TRY(ws_get(c, &b->iou4, (size_t)8, "dec iou"));
+  SAMPT_TRY(ws_get(c, &b->part, (size_t)Tmax * 8 * ((GG + 255) / 256) * 18, "dec attn partials"));
   return 0;
 }
 
@@ -738,40 +827,175 @@ extern "C" int sampt_sam_predict(sampt_ctx* ctx, const float* feat_tok, int G, c
 // n_pos_first: if > 0, a first call uses only the first n_pos_first (positive) points and feeds its low-res mask to the
 // second call (sam_pt.py:792-807); 0 = single initial call (:783-790).
 // outputs: logits [H,W], iou [1], low_res [256,256], n_refine_done [1] (int, device).
+namespace sampt {
+
+struct RefineShape { int G, K, npos, nref, in_h, in_w, H, W; };
+struct RefinePtrs {
+  const float* feat_tok; const float* coords; const int* labels; const float* pos_coords; const int* pos_labels;
+  float* logits; float* iou; float* low_res; int* n_done; int* bbox; int* skip; float* box;
+};
+
+// enqueue the whole predict_mask chain (sam_pt.py:781-828) on `st`
+static int enqueue_refine_chain(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, const RefineShape& s, const RefinePtrs& p) {
+  init_ctl_kernel<<<1, 1, 0, st>>>(p.bbox, p.skip, p.n_done);
+  c->launches++;
+  DecodeCall d{};
+  d.feat_tok = p.feat_tok; d.n_masks = 1; d.tok0 = 0; d.in_h = s.in_h; d.in_w = s.in_w; d.H = s.H; d.W = s.W;
+  d.logits = p.logits; d.iou = p.iou; d.low_res = p.low_res; d.skip = nullptr;
+  if (s.npos > 0) {
+    d.coords = p.pos_coords; d.labels = p.pos_labels; d.K = s.npos; d.box = nullptr; d.use_box = 0; d.mask_in = nullptr; d.bbox = nullptr;
+    SAMPT_TRY(decode_once(c, st, w, b, d, s.G));
+    d.mask_in = p.low_res;
+  }
+  d.coords = p.coords; d.labels = p.labels; d.K = s.K; d.box = nullptr; d.use_box = 0; d.bbox = p.bbox;
+  if (s.npos <= 0) d.mask_in = nullptr;
+  SAMPT_TRY(decode_once(c, st, w, b, d, s.G));
+  for (int it = 0; it < s.nref; ++it) {
+    refine_ctl_kernel<<<1, 1, 0, st>>>(p.bbox, p.box, p.skip, p.n_done);
+    c->launches++;
+    d.box = p.box; d.use_box = 1; d.mask_in = p.low_res; d.skip = p.skip;
+    SAMPT_TRY(decode_once(c, st, w, b, d, s.G));
+  }
+  SAMPT_LAUNCH_CHECK();
+  return 0;
+}
+
+// One captured CUDA graph per chain shape: the ~500 kernels of a frame's 13 predict_torch calls replay as ONE launch.
+// The graph works on buffers carved from the decoder slab (stable addresses); inputs/outputs are staged with D2D copies.
+struct RefineGraph {
+  RefineShape shape;
+  DecBufs bufs;
+  float *feat, *coords, *pos_coords, *logits, *iou, *low, *box;
+  int *labels, *pos_labels, *n_done, *bbox, *skip;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+
+static void* dec_alloc(Ctx* c, size_t bytes) {
+  size_t a = (c->dec_off + 255) & ~size_t(255);
+  if (a + bytes > c->dec_bytes) return nullptr;
+  c->dec_off = a + bytes;
+  return c->dec_base + a;
+}
+template <typename T>
+static int dec_get(Ctx* c, T** out, size_t count, const char* what) {
+  *out = reinterpret_cast<T*>(dec_alloc(c, count * sizeof(T)));
+  if (!*out) { set_error("decoder workspace exhausted allocating %s", what); return -3; }
+  return 0;
+}
+
+static int build_refine_graph(Ctx* c, DecW& w, const RefineShape& s, RefineGraph** out) {
+  RefineGraph* g = new RefineGraph();
+  g->shape = s;
+  const int GG = s.G * s.G, Tmax = w.n_out_tok + s.K + 2;
+  DecBufs& b = g->bufs;
+  SAMPT_TRY(dec_get(c, &b.tokens, (size_t)Tmax * 256, "tokens")); SAMPT_TRY(dec_get(c, &b.queries, (size_t)Tmax * 256, "queries"));
+  SAMPT_TRY(dec_get(c, &b.qpe, (size_t)Tmax * 256, "qpe")); SAMPT_TRY(dec_get(c, &b.tq, (size_t)Tmax * 256, "tq"));
+  SAMPT_TRY(dec_get(c, &b.tk, (size_t)Tmax * 256, "tk")); SAMPT_TRY(dec_get(c, &b.tv, (size_t)Tmax * 256, "tv"));
+  SAMPT_TRY(dec_get(c, &b.ta, (size_t)Tmax * 256, "ta")); SAMPT_TRY(dec_get(c, &b.tmp, (size_t)Tmax * 256, "tmp"));
+  SAMPT_TRY(dec_get(c, &b.mlp_h, (size_t)Tmax * 2048, "mlp_h"));
+  SAMPT_TRY(dec_get(c, &b.src, (size_t)GG * 256, "src")); SAMPT_TRY(dec_get(c, &b.keys, (size_t)GG * 256, "keys"));
+  SAMPT_TRY(dec_get(c, &b.ik, (size_t)GG * 128, "ik")); SAMPT_TRY(dec_get(c, &b.iv, (size_t)GG * 128, "iv"));
+  SAMPT_TRY(dec_get(c, &b.iq, (size_t)GG * 128, "iq")); SAMPT_TRY(dec_get(c, &b.ia, (size_t)GG * 128, "ia"));
+  SAMPT_TRY(dec_get(c, &b.u1, (size_t)GG * 256, "u1")); SAMPT_TRY(dec_get(c, &b.hyper, (size_t)128, "hyper"));
+  SAMPT_TRY(dec_get(c, &b.iou4, (size_t)8, "iou4"));
+  SAMPT_TRY(dec_get(c, &b.part, (size_t)Tmax * 8 * ((GG + 255) / 256) * 18, "attn partials"));
+  SAMPT_TRY(dec_get(c, &g->feat, (size_t)GG * 256, "feat stage"));
+  SAMPT_TRY(dec_get(c, &g->coords, (size_t)std::max(1, s.K) * 2, "coords")); SAMPT_TRY(dec_get(c, &g->labels, (size_t)std::max(1, s.K), "labels"));
+  SAMPT_TRY(dec_get(c, &g->pos_coords, (size_t)std::max(1, s.npos) * 2, "pos coords"));
+  SAMPT_TRY(dec_get(c, &g->pos_labels, (size_t)std::max(1, s.npos), "pos labels"));
+  SAMPT_TRY(dec_get(c, &g->logits, (size_t)s.H * s.W, "logits stage"));
+  SAMPT_TRY(dec_get(c, &g->iou, (size_t)8, "iou")); SAMPT_TRY(dec_get(c, &g->low, (size_t)16 * GG, "low_res"));
+  SAMPT_TRY(dec_get(c, &g->n_done, (size_t)8, "n_done")); SAMPT_TRY(dec_get(c, &g->bbox, (size_t)8, "bbox"));
+  SAMPT_TRY(dec_get(c, &g->skip, (size_t)8, "skip")); SAMPT_TRY(dec_get(c, &g->box, (size_t)8, "box"));
+  RefinePtrs p{g->feat, g->coords, g->labels, g->pos_coords, g->pos_labels, g->logits, g->iou, g->low, g->n_done, g->bbox, g->skip, g->box};
+  if (!c->cap_stream) SAMPT_CUDA(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+  // eager warm-up on the capture stream (sets function attributes, touches every code path), then capture.
+  // cap_stream does not synchronise with the legacy default stream: make sure pending weight uploads have landed.
+  SAMPT_CUDA(cudaDeviceSynchronize());
+  SAMPT_CUDA(cudaMemsetAsync(g->feat, 0, (size_t)GG * 256 * sizeof(float), c->cap_stream));
+  SAMPT_CUDA(cudaMemsetAsync(g->coords, 0, (size_t)std::max(1, s.K) * 2 * sizeof(float), c->cap_stream));
+  SAMPT_CUDA(cudaMemsetAsync(g->labels, 0, (size_t)std::max(1, s.K) * sizeof(int), c->cap_stream));
+  SAMPT_CUDA(cudaMemsetAsync(g->pos_coords, 0, (size_t)std::max(1, s.npos) * 2 * sizeof(float), c->cap_stream));
+  SAMPT_CUDA(cudaMemsetAsync(g->pos_labels, 0, (size_t)std::max(1, s.npos) * sizeof(int), c->cap_stream));
+  const long long l0 = c->launches;
+  SAMPT_TRY(enqueue_refine_chain(c, c->cap_stream, w, b, s, p));
+  SAMPT_CUDA(cudaStreamSynchronize(c->cap_stream));
+  g->launches = c->launches - l0;
+  SAMPT_CUDA(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed));
+  int rc = enqueue_refine_chain(c, c->cap_stream, w, b, s, p);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
+  c->launches -= g->launches;  // the capture pass did not execute anything
+  if (rc != 0) return rc;
+  SAMPT_CHECK(e == cudaSuccess && graph != nullptr, "stream capture of the decode chain failed: %s", cudaGetErrorString(e));
+  SAMPT_CUDA(cudaGraphInstantiate(&g->exec, graph, 0));
+  cudaGraphDestroy(graph);
+  *out = g;
+  return 0;
+}
+
+}  // namespace sampt
+
+extern "C" int sampt_ctx_set_decoder_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  for (auto& kv : c->graph_cache) {
+    RefineGraph* g = reinterpret_cast<RefineGraph*>(kv.second);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    delete g;
+  }
+  c->graph_cache.clear();
+  c->dec_base = reinterpret_cast<char*>(dev_ptr);
+  c->dec_bytes = bytes;
+  c->dec_off = 0;
+  return 0;
+}
+
 extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const float* coords, const int* labels, int K,
                                         const float* pos_coords, const int* pos_labels, int n_pos_first, int n_refine, int in_h,
                                         int in_w, int H, int W, float* logits, float* iou, float* low_res, int* n_refine_done,
                                         void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  c->ws_reset();
   DecW w;
   SAMPT_TRY(load_dec(c, &w));
-  DecBufs b;
-  SAMPT_TRY(alloc_dec_bufs(c, &b, w.n_out_tok + K + 2, G * G));
-  int *bbox, *skip; float* box;
-  SAMPT_TRY(ws_get(c, &bbox, 8, "bbox"));
-  SAMPT_TRY(ws_get(c, &skip, 1, "skip"));
-  SAMPT_TRY(ws_get(c, &box, 4, "box"));
-  init_ctl_kernel<<<1, 1, 0, st>>>(bbox, skip, n_refine_done);
-  c->launches++;
-  DecodeCall d{};
-  d.feat_tok = feat_tok; d.n_masks = 1; d.tok0 = 0; d.in_h = in_h; d.in_w = in_w; d.H = H; d.W = W;
-  d.logits = logits; d.iou = iou; d.low_res = low_res; d.skip = nullptr;
-  if (n_pos_first > 0) {
-    d.coords = pos_coords; d.labels = pos_labels; d.K = n_pos_first; d.box = nullptr; d.use_box = 0; d.mask_in = nullptr; d.bbox = nullptr;
-    SAMPT_TRY(decode_once(c, st, w, b, d, G));
-    d.mask_in = low_res;
+  RefineShape s{G, K, n_pos_first > 0 ? n_pos_first : 0, n_refine, in_h, in_w, H, W};
+  if (c->dec_base == nullptr) {
+    // eager path (no decoder slab registered): buffers from the shared workspace, kernels launched one by one
+    c->ws_reset();
+    DecBufs b;
+    SAMPT_TRY(alloc_dec_bufs(c, &b, w.n_out_tok + K + 2, G * G));
+    int *bbox, *skip; float* box;
+    SAMPT_TRY(ws_get(c, &bbox, 8, "bbox"));
+    SAMPT_TRY(ws_get(c, &skip, 1, "skip"));
+    SAMPT_TRY(ws_get(c, &box, 4, "box"));
+    RefinePtrs p{feat_tok, coords, labels, pos_coords, pos_labels, logits, iou, low_res, n_refine_done, bbox, skip, box};
+    return enqueue_refine_chain(c, st, w, b, s, p);
   }
-  d.coords = coords; d.labels = labels; d.K = K; d.box = nullptr; d.use_box = 0; d.bbox = bbox;
-  if (n_pos_first <= 0) d.mask_in = nullptr;
-  SAMPT_TRY(decode_once(c, st, w, b, d, G));
-  for (int it = 0; it < n_refine; ++it) {
-    refine_ctl_kernel<<<1, 1, 0, st>>>(bbox, box, skip, n_refine_done);
-    c->launches++;
-    d.box = box; d.use_box = 1; d.mask_in = low_res; d.skip = skip;
-    SAMPT_TRY(decode_once(c, st, w, b, d, G));
+  std::vector<int> key{G, K, s.npos, n_refine, in_h, in_w, H, W, w.n_out_tok};
+  RefineGraph* g = nullptr;
+  auto it = c->graph_cache.find(key);
+  if (it == c->graph_cache.end()) {
+    // weights may not change between capture and replay: the cache is dropped by sampt_ctx_set_decoder_workspace,
+    // which the Python side calls whenever SAM's decoder weights are (re)registered
+    SAMPT_TRY(build_refine_graph(c, w, s, &g));
+    c->graph_cache[key] = g;
+  } else {
+    g = reinterpret_cast<RefineGraph*>(it->second);
   }
-  SAMPT_LAUNCH_CHECK();
+  const int GG = G * G;
+  SAMPT_CUDA(cudaMemcpyAsync(g->feat, feat_tok, (size_t)GG * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(g->coords, coords, (size_t)K * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(g->labels, labels, (size_t)K * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (s.npos > 0) {
+    SAMPT_CUDA(cudaMemcpyAsync(g->pos_coords, pos_coords, (size_t)s.npos * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SAMPT_CUDA(cudaMemcpyAsync(g->pos_labels, pos_labels, (size_t)s.npos * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
+  SAMPT_CUDA(cudaGraphLaunch(g->exec, st));
+  c->launches += g->launches;
+  SAMPT_CUDA(cudaMemcpyAsync(logits, g->logits, (size_t)H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(iou, g->iou, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(low_res, g->low, (size_t)16 * GG * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (n_refine_done) SAMPT_CUDA(cudaMemcpyAsync(n_refine_done, g->n_done, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return 0;
 }

@@ -123,6 +123,59 @@ sgemm_nt_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ 
   }
 }
 
+// Small-M variant (M <= MAXM rows, e.g. the prompt tokens of the mask decoder or the N*S rows of the PIPS mixer):
+// weight-bandwidth bound, so the grid is spread over the N (output column) axis and every weight row is read exactly once,
+// coalesced.  One warp = one output column x all M rows; lanes split K (float4 per lane per step); X is staged through
+// shared memory in K chunks of 128; a warp-shuffle reduction per row finishes the dot products.
+template <int MAXM>
+__global__ void __launch_bounds__(256)
+sgemm_smallm_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                    const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
+  if (skip != nullptr && *skip != 0) return;
+  constexpr int KC = 128;
+  __shared__ __align__(16) float xs[MAXM][KC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  float acc[MAXM];
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < MAXM * (KC / 4); i += 256) {
+      int m = i / (KC / 4), c = (i % (KC / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && k0 + c < K) v = *reinterpret_cast<const float4*>(X + (size_t)m * ldx + k0 + c);
+      *reinterpret_cast<float4*>(&xs[m][c]) = v;
+    }
+    __syncthreads();
+    if (n < N) {
+      const int kk = k0 + lane * 4;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kk < K) w = *reinterpret_cast<const float4*>(W + (size_t)n * ldw + kk);
+#pragma unroll
+      for (int m = 0; m < MAXM; ++m) {
+        float4 x = *reinterpret_cast<const float4*>(&xs[m][lane * 4]);
+        acc[m] = fmaf(w.x, x.x, acc[m]);
+        acc[m] = fmaf(w.y, x.y, acc[m]);
+        acc[m] = fmaf(w.z, x.z, acc[m]);
+        acc[m] = fmaf(w.w, x.w, acc[m]);
+      }
+    }
+  }
+  if (n >= N) return;
+#pragma unroll
+  for (int m = 0; m < MAXM; ++m) {
+    float v = warp_sum(acc[m]);
+    if (lane == (m & 31) && m < M) {
+      if (bias) v += bias[n];
+      if (act == 1) v = gelu_erf(v);
+      else if (act == 2) v = fmaxf(v, 0.f);
+      if (residual) v += residual[(size_t)m * ldr + n];
+      Y[(size_t)m * ldy + n] = v;
+    }
+  }
+}
+
 int sgemm_nt(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
              const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act) {
   return sgemm_nt_skip(c, st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, nullptr);
@@ -132,17 +185,25 @@ int sgemm_nt_skip(Ctx* c, cudaStream_t st, const float* X, int ldx, const float*
                   const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
   SAMPT_CHECK((K % 4) == 0 && (ldx % 4) == 0 && (ldw % 4) == 0, "sgemm_nt: K/ldx/ldw must be multiples of 4 (K=%d ldx=%d ldw=%d)", K, ldx, ldw);
   if (M <= 0 || N <= 0) return 0;
-  // tile choice: big tiles when there is enough work to fill 148 SMs, else smaller tiles for more CTAs
-  long long tiles_big = (long long)cdiv(M, 128) * cdiv(N, 64);
-  if (tiles_big >= 2 * c->num_sms) {
-    dim3 grid(cdiv(N, 64), cdiv(M, 128));
-    sgemm_nt_kernel<128, 64, 16, 8, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
-  } else if ((long long)cdiv(M, 64) * cdiv(N, 64) >= c->num_sms) {
-    dim3 grid(cdiv(N, 64), cdiv(M, 64));
-    sgemm_nt_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+  if (M <= 16) {
+    sgemm_smallm_kernel<16><<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+  } else if (M <= 32) {
+    sgemm_smallm_kernel<32><<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+  } else if (M <= 64) {
+    sgemm_smallm_kernel<64><<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   } else {
-    dim3 grid(cdiv(N, 16), cdiv(M, 32));
-    sgemm_nt_kernel<32, 16, 16, 4, 4><<<grid, 32, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+    // tile choice: the largest tile that still yields ~a wave of CTAs on 148 SMs
+    const long long t128 = (long long)cdiv(M, 128) * cdiv(N, 64), t64 = (long long)cdiv(M, 64) * cdiv(N, 64);
+    if (t128 >= c->num_sms) {
+      dim3 grid(cdiv(N, 64), cdiv(M, 128));
+      sgemm_nt_kernel<128, 64, 16, 8, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+    } else if (t64 >= c->num_sms / 2) {
+      dim3 grid(cdiv(N, 64), cdiv(M, 64));
+      sgemm_nt_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+    } else {
+      dim3 grid(cdiv(N, 32), cdiv(M, 32));
+      sgemm_nt_kernel<32, 32, 16, 4, 4><<<grid, 64, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+    }
   }
   c->launches++;
   SAMPT_LAUNCH_CHECK();

@@ -129,9 +129,20 @@ class SamPt(nn.Module):
     @torch.no_grad()
     def _apply_sam_to_trajectories(self, images, trajectories, visibilities):
         """reference sam_pt.py:694-866.  images (T,3,H,W) uint8 on the device."""
-        n_frames, _, height, width = images.shape
-        _, n_masks, points_per_mask, _ = trajectories.shape
-        assert trajectories.shape == (n_frames, n_masks, points_per_mask, 2)
+        n_frames = images.shape[0]
+        logits, scores_pf, counted = self._apply_sam_to_frames(images, list(range(n_frames)), trajectories, visibilities)
+        counted_d = counted.to(self.device)
+        cnt = counted_d.sum(dim=0).clamp(min=1)
+        pred_scores = torch.where(counted_d, scores_pf, torch.zeros_like(scores_pf)).sum(dim=0) / cnt
+        return pred_scores, logits, scores_pf
+
+    @torch.no_grad()
+    def _apply_sam_to_frames(self, images, frame_ids, trajectories, visibilities):
+        """SAM on a subset of frames: images (n,3,H,W) uint8 on the device are the frames `frame_ids` of the clip whose
+        full-clip trajectories (T,M,P,2) / visibilities (T,M,P) are given.  Returns logits (M,n,H,W), scores (n,M) on the
+        device and `counted` (n,M) bool on the host (frames with at least one visible point)."""
+        n_sub, _, height, width = images.shape
+        n_frames, n_masks, points_per_mask, _ = trajectories.shape
         assert visibilities.shape == (n_frames, n_masks, points_per_mask)
         dev = self.device
         pred = self.sam_predictor
@@ -157,18 +168,19 @@ class SamPt(nn.Module):
                 labels = np.concatenate([labels, np.zeros((len(other)), dtype=int)], axis=0)
             return coords, labels
 
-        logits = torch.full((n_masks, n_frames, height, width), -float("inf"), device=dev, dtype=torch.float32)
-        scores_pf = torch.full((n_frames, n_masks), -float("inf"), device=dev, dtype=torch.float32)
-        counted = torch.zeros((n_frames, n_masks), dtype=torch.bool)
+        logits = torch.full((n_masks, n_sub, height, width), -float("inf"), device=dev, dtype=torch.float32)
+        scores_pf = torch.full((n_sub, n_masks), -float("inf"), device=dev, dtype=torch.float32)
+        counted = torch.zeros((n_sub, n_masks), dtype=torch.bool)
         n_ref = int(self.iterative_refinement_iterations) if self.iterative_refinement_iterations else 0
         B = max(1, int(self.encoder_batch))
         want_interm = pred._uses_interm()
-        for f0 in range(0, n_frames, B):
+        for f0 in range(0, n_sub, B):
             chunk = images[f0:f0 + B]
             enc = pred.encode_frames(chunk, want_interm=want_interm)
             feats, interm = enc if want_interm else (enc, None)
             for j in range(chunk.shape[0]):
-                f = f0 + j
+                i = f0 + j
+                f = frame_ids[i]
                 pred.set_frames_features((height, width), (feats[j:j + 1], interm[j:j + 1]) if want_interm else feats[j:j + 1])
                 for m in range(n_masks):
                     coords, labels = prepare_points(f, m)
@@ -176,13 +188,80 @@ class SamPt(nn.Module):
                         continue  # all points invisible -> mask stays -inf, score -inf (sam_pt.py:766-767,855)
                     c1024 = torch.as_tensor(pred.transform.apply_coords(coords, pred.original_size), dtype=torch.float, device=dev)
                     lab = torch.as_tensor(labels, dtype=torch.int, device=dev)
-                    iou, _, _ = pred.predict_refine(c1024, lab, 1 if self.negative_points_per_mask > 0 else 0, n_ref, logits[m, f])
+                    iou, _, _ = pred.predict_refine(c1024, lab, 1 if self.negative_points_per_mask > 0 else 0, n_ref, logits[m, i])
                     # "Mask is empty if SAM's IoU score is too low" (sam_pt.py:833-835), without a host round trip
-                    logits[m, f] = torch.where(iou[0] < self.sam_iou_threshold, torch.full_like(logits[m, f], -float("inf")),
-                                               logits[m, f])
-                    scores_pf[f, m] = iou[0]
-                    counted[f, m] = True
-        counted_d = counted.to(dev)
-        cnt = counted_d.sum(dim=0).clamp(min=1)
-        pred_scores = torch.where(counted_d, scores_pf, torch.zeros_like(scores_pf)).sum(dim=0) / cnt
-        return pred_scores, logits, scores_pf
+                    logits[m, i] = torch.where(iou[0] < self.sam_iou_threshold, torch.full_like(logits[m, i], -float("inf")),
+                                               logits[m, i])
+                    scores_pf[i, m] = iou[0]
+                    counted[i, m] = True
+        return logits, scores_pf, counted
+
+    # ------------------------------------------------------------------------------------------------ multi-GPU
+    @torch.no_grad()
+    def forward_clips_sharded(self, videos, gather_logits: bool = False):
+        """Frame-sharded processing of `len(videos)` clips across the ranks of the default process group:
+        rank r owns frames {f : f mod G == r} of EVERY clip.
+          A. local : PIPS encoder (fnet) on the owned frames of every clip
+          B. NCCL  : ONE all-gather of the fp32 feature maps (13 MB/frame @480x854) -> every rank holds all features
+          C. local : linked tracker chain of clip c on rank c mod G (pyramid built locally after the gather)
+          D. NCCL  : all-gather of the (T,N,3) trajectories/visibilities (a few KB)
+          E. local : SAM encode + prompt/mask decode on the owned frames of every clip
+        Returns, per clip, {"trajectories","visibilities","logits" (M, n_owned, H, W), "frame_ids", "scores_per_frame"}
+        (logits stay sharded unless gather_logits)."""
+        import torch.distributed as dist
+        from sampt_b200 import sharding
+        world, rank = dist.get_world_size(), dist.get_rank()
+        dev = self.device
+        trk = self.point_tracker.to(dev)
+        C = len(videos)
+        T = len(videos[0]["image"])
+        own = sharding.owned_frames(T, rank, world)
+        # A. upload only the owned frames, encode them
+        own_frames, local_fm = [], []
+        for v in videos:
+            fr = torch.stack([v["image"][f].to(dev, non_blocking=True) for f in own], dim=0)
+            own_frames.append(fr)
+            local_fm.append(trk.model.fnet_frames(fr))
+        local = torch.stack(local_fm, dim=1)  # (n_own, C, H4, W4, 128): frame-major so one collective serves all clips
+        # B. the exchange step
+        full = sharding.allgather_frames(local, T)  # (T, C, H4, W4, 128)
+        # C. chains: clip c on rank c % world
+        results = [None] * C
+        tv_local = []
+        shapes = []
+        for c, v in enumerate(videos):
+            q = v["query_points"]
+            M, P, _ = q.shape
+            shapes.append((M, P))
+            if c % world == rank:
+                pyr = trk.model.build_pyramid(full[:, c].contiguous())
+                traj, vis = trk.track_on_features(pyr, q.reshape(1, M * P, 3).to(dev))
+                tv_local.append(torch.cat([traj[0], vis[0].float()[..., None]], dim=-1))  # (T, N, 3)
+        del full
+        # D. share the trajectories (tiny)
+        N_max = max(m * p for m, p in shapes)
+        mine = torch.zeros((len(range(rank, C, world)), T, N_max, 3), device=dev)
+        for i, t in enumerate(tv_local):
+            mine[i, :, : t.shape[1]] = t
+        n_slots = (C + world - 1) // world
+        slab = torch.zeros((n_slots, T, N_max, 3), device=dev)
+        slab[: mine.shape[0]] = mine
+        gathered = torch.empty((world * n_slots, T, N_max, 3), device=dev)
+        dist.all_gather_into_tensor(gathered, slab)
+        # E. SAM on the owned frames
+        h, w = own_frames[0].shape[-2:]
+        for c, v in enumerate(videos):
+            M, P = shapes[c]
+            tv = gathered[(c % world) * n_slots + c // world, :, : M * P]
+            traj = tv[..., :2].reshape(T, M, P, 2)
+            vis = tv[..., 2].reshape(T, M, P)
+            out_code = float(PointVisibilityType.OUTSIDE_FRAME.value)
+            oob = (traj[..., 0] / w < 0.01) | (traj[..., 1] / h < 0.01) | (traj[..., 0] / w > 0.99) | (traj[..., 1] / h > 0.99)
+            vis = torch.where(oob, torch.full_like(vis, out_code), vis)
+            logits, spf, _ = self._apply_sam_to_frames(own_frames[c], own, traj, vis)
+            res = {"trajectories": traj, "visibilities": vis, "logits": logits, "frame_ids": own, "scores_per_frame": spf}
+            if gather_logits:
+                res["logits"] = sharding.allgather_frames(logits.transpose(0, 1).contiguous(), T).transpose(0, 1)
+                res["frame_ids"] = list(range(T))
+            results[c] = res
+        return results

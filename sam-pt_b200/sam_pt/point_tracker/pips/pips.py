@@ -84,22 +84,32 @@ class Pips(nn.Module):
         return ctx
 
     # ------------------------------------------------------------------ building blocks used by the tracker
-    def encode_frames(self, frames_u8: torch.Tensor):
-        """(T,3,H,W) uint8 -> channels-last pyramid [(T,H/4,W/4,128), /2, /4, /8] (fnet once per frame + CorrBlock pyramid)."""
+    def fnet_frames(self, frames_u8: torch.Tensor) -> torch.Tensor:
+        """(n,3,H,W) uint8 -> channels-last encoder features (n,H/4,W/4,128) fp32 (BasicEncoder, once per frame)."""
         assert frames_u8.dtype == torch.uint8 and frames_u8.is_cuda
         if self.stride != 4:
             raise NotImplementedError("the B200 PIPS path is built for stride 4 (configs/model/point_tracker/pips.yaml:3)")
         ctx = self.native_context()
-        T, _, H, W = frames_u8.shape
-        H4, W4 = H // 4, W // 4
-        dev = frames_u8.device
-        pyr = [torch.empty((T, H4 >> l, W4 >> l, LATENT), device=dev, dtype=torch.float32) for l in range(4)]
-        L = native.lib()
-        native.check(L.sampt_pips_fnet(ctx.handle, native.ptr(frames_u8.contiguous()), c_int(T), c_int(H), c_int(W), c_int(4),
-                                       native.ptr(pyr[0]), native.stream_ptr()), "pips_fnet")
-        native.check(L.sampt_pips_pyramid(ctx.handle, native.ptr(pyr[0]), c_int(T), c_int(H4), c_int(W4), native.ptr(pyr[1]),
-                                          native.ptr(pyr[2]), native.ptr(pyr[3]), native.stream_ptr()), "pips_pyramid")
+        n, _, H, W = frames_u8.shape
+        fm = torch.empty((n, H // 4, W // 4, LATENT), device=frames_u8.device, dtype=torch.float32)
+        native.check(native.lib().sampt_pips_fnet(ctx.handle, native.ptr(frames_u8.contiguous()), c_int(n), c_int(H), c_int(W),
+                                                  c_int(4), native.ptr(fm), native.stream_ptr()), "pips_fnet")
+        return fm
+
+    def build_pyramid(self, fmaps: torch.Tensor):
+        """(T,H4,W4,128) -> [level0, /2, /4, /8] (CorrBlock.__init__ avg-pool pyramid, pips.py:355-361)."""
+        ctx = self.native_context()
+        T, H4, W4, _ = fmaps.shape
+        pyr = [fmaps.contiguous()] + [torch.empty((T, H4 >> l, W4 >> l, LATENT), device=fmaps.device, dtype=torch.float32)
+                                      for l in range(1, 4)]
+        native.check(native.lib().sampt_pips_pyramid(ctx.handle, native.ptr(pyr[0]), c_int(T), c_int(H4), c_int(W4),
+                                                     native.ptr(pyr[1]), native.ptr(pyr[2]), native.ptr(pyr[3]),
+                                                     native.stream_ptr()), "pips_pyramid")
         return pyr
+
+    def encode_frames(self, frames_u8: torch.Tensor):
+        """(T,3,H,W) uint8 -> channels-last pyramid [(T,H/4,W/4,128), /2, /4, /8] (fnet once per frame + CorrBlock pyramid)."""
+        return self.build_pyramid(self.fnet_frames(frames_u8))
 
     def track(self, pyr, query_points: torch.Tensor, thr0: float, iters: int = 6, flip: bool = False,
               max_windows: int = 0):

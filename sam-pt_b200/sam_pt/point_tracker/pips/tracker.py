@@ -35,9 +35,15 @@ class PipsPointTracker(PointTracker):
         frames = rgbs[0].to(dev)
         if frames.dtype != torch.uint8:
             frames = frames.round().clamp(0, 255).to(torch.uint8)
-        q = query_points[0].float().to(dev)
-        T = frames.shape[0]
         pyr = self.model.encode_frames(frames)
+        return self.track_on_features(pyr, query_points)
+
+    def track_on_features(self, pyr, query_points):
+        """The linked bidirectional chain on pre-computed feature pyramids (used directly by the frame-sharded multi-GPU
+        path, where the per-frame features arrive through an all-gather)."""
+        dev = self.device
+        q = query_points[0].float().to(dev)
+        T = pyr[0].shape[0]
         thr = float(self.initial_next_frame_visibility_threshold)
         traj_r, vis_r = self.model.track(pyr, q, thr, iters=6, flip=False)
         start = q[:, 0].long()

@@ -1,6 +1,7 @@
 """`Sam` (upstream segment_anything/modeling/sam.py @ aac76a1): holds the three sub-modules + pixel statistics; the
 reference sub-classes it as SamHydra (sam_pt/modeling/sam.py:34-41).  Here it also owns the registration of every weight
 with libsampt_b200 in kernel-native layout."""
+import os
 from typing import List
 
 import torch
@@ -22,6 +23,7 @@ class Sam(nn.Module):
         self.register_buffer("pixel_mean", torch.tensor(list(pixel_mean), dtype=torch.float32).view(-1, 1, 1), False)
         self.register_buffer("pixel_std", torch.tensor(list(pixel_std), dtype=torch.float32).view(-1, 1, 1), False)
         self._dec_registered = None
+        self.use_cuda_graphs = os.environ.get("SAMPT_DECODE_GRAPHS", "1") != "0"
 
     @property
     def device(self):
@@ -34,6 +36,8 @@ class Sam(nn.Module):
                tuple(p._version for p in self.mask_decoder.parameters()), self.device)
         if self._dec_registered != key:
             self._register_decoder(ctx)
+            if self.use_cuda_graphs:
+                ctx.set_decoder_workspace()  # also invalidates graphs captured with the previous weights
             self._dec_registered = key
         return ctx
 

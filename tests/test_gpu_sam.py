@@ -147,3 +147,28 @@ def test_sampt_c1_end_to_end(tmp_path):
     assert np.allclose(np.array(out["scores"]), np.array(ref["scores"]), atol=2e-3)
     # reference invariants: background logits are finite where masks exist; output shapes (sam_pt.py:222-226)
     assert out["logits"][0].shape == (2, 240, 320)
+
+
+def test_precision_dial_report(tmp_path):
+    """Records mask IoU vs the oracle for the three ViT precision settings on C1 (documentation for DESIGN.md §5);
+    only the parity-validated setting (3) is asserted."""
+    import json
+    import os
+    cfg = sam_ref.VIT_B
+    sam_sd = _sam_sd(cfg, 7202)
+    pips_sd = synth.condition_pips(synth.make_state_dict(pips_ref.pips_state_dict_shapes(), 7201))
+    ckpt = synth.write_pips_checkpoint_dir(pips_sd, str(tmp_path / "pips"))
+    video = synth.make_video_dict(2, 240, 320, 4)
+    ref = sampt_ref.sampt_forward(pips_sd, sam_ref.RefSamPredictor(sam_sd, cfg), video, positive_points_per_mask=4,
+                                  sam_iou_threshold=-1e9)
+    model = factory.build_sam_pt("vit_b", sam_sd, ckpt, positive_points_per_mask=4, sam_iou_threshold=-1e9)
+    report = {}
+    for p in (1, 2, 3):
+        model.sam_predictor.model.image_encoder.precision = p
+        out = model(video)
+        report[p] = [_iou(out["logits"][0][f].cpu(), ref["logits"][0][f]) for f in range(2)]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "precision_dial_c1.json"), "w") as fh:
+        json.dump({"config": "C1 (2x240x320, ViT-B + PIPS, 4 pts), per-frame mask IoU vs CPU oracle", "iou_by_precision": report}, fh)
+    assert min(report[3]) >= 0.999
