@@ -34,6 +34,7 @@ CONFIGS = {
     "C1": (2, 240, 320, "vit_b", 4),
     "C2": (50, 480, 854, "vit_h", 8),
     "C2b": (50, 480, 854, "vit_b", 8),
+    "C2p": (4, 480, 854, "vit_h", 8),   # profiling-sized slice of C2 (ncu launch lists)
 }
 SAM_SEED, PIPS_SEED = 7202, 7201
 
@@ -185,6 +186,8 @@ def run_ours(args):
     ms, ms_e2e = t.tolist()
 
     breakdown = stage_breakdown(model, frames_dev, q_dev) if args.breakdown else None
+    if args.kernel_table and rank == 0:
+        kernel_table(lambda: step_resident(frames_dev, q_dev), args.kernel_table)
     # ---------------- roofline of the dominant kernel (ViT tcgen05 GEMM), measured live with CUDA events
     roof = gemm_roofline(model, dev, args)
     cpu_base = None
@@ -196,7 +199,7 @@ def run_ours(args):
             "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
             "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 hi+lo activations (fp32 accumulate)", 3: "f16 hi+lo split x3 (~fp32)"}[args.precision]
+            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split x3 (~fp32)"}[args.precision]
                      + " ViT; f32 PIPS + decoder",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS (S=8, stride 4), 1 mask x {P} points, "
@@ -271,7 +274,7 @@ def run_ours_frame_sharded(args, model, dev, rank, world, local):
             "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
             "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 hi+lo activations (fp32 accumulate)", 3: "f16 hi+lo split x3 (~fp32)"}[args.precision]
+            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split x3 (~fp32)"}[args.precision]
                      + " ViT; f32 PIPS + decoder",
             "data": "synthetic",
             "config": {"workload": f"{world} x {args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS, 1 mask x {P} points, 12 refinements; "
@@ -285,6 +288,30 @@ def run_ours_frame_sharded(args, model, dev, rank, world, local):
         }
         print(json.dumps(line))
     dist.destroy_process_group()
+
+
+def kernel_table(step_fn, path):
+    """Per-kernel device time of one step via CUPTI (torch.profiler sees every kernel of the process, including the ones
+    launched through the C ABI).  Not a bench value; written for profiles/."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step_fn()
+        torch.cuda.synchronize()
+    rows = []
+    for e in prof.key_averages():
+        t = getattr(e, "device_time_total", None)
+        if t is None:
+            t = getattr(e, "cuda_time_total", 0.0)
+        if t > 0:
+            rows.append((e.key, e.count, t))
+    rows.sort(key=lambda r: -r[2])
+    tot = sum(r[2] for r in rows)
+    with open(path, "w") as f:
+        f.write(f"# per-kernel device time of one step (CUPTI via torch.profiler); total {tot / 1e3:.2f} ms\n\n")
+        f.write("| kernel | launches | total ms | mean us | share |\n|---|---:|---:|---:|---:|\n")
+        for k, c, t in rows[:60]:
+            f.write(f"| `{k[:110]}` | {c} | {t / 1e3:.2f} | {t / c:.1f} | {100 * t / tot:.1f}% |\n")
 
 
 def stage_breakdown(model, frames_dev, q_dev):
@@ -335,7 +362,7 @@ def gemm_roofline(model, dev, args):
     D, B = enc.embed_dim, args.encoder_batch
     M, N, K = B * 4096, 4 * D, D
     p = args.precision
-    asp, bsp = (2 if p >= 2 else 1), (2 if p >= 3 else 1)
+    asp, bsp = (2 if p >= 3 else 1), (2 if p >= 2 else 1)
     A = torch.randn((M, K * asp), device=dev).half()
     Wt = torch.randn((N, K * bsp), device=dev).half()
     out = torch.empty((M, N), device=dev, dtype=torch.float16)
@@ -418,6 +445,7 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true")
+    ap.add_argument("--kernel-table", default=None, help="write a per-kernel time table of one step (CUPTI) to this path")
     ap.add_argument("--mgpu-mode", default="frame_shard", choices=["frame_shard", "clip_per_gpu"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -75,8 +75,8 @@ int sampt_linear_f32(sampt_ctx* ctx, const float* X, int ldx, const float* W, in
 /* ---- tensor-core GEMM (tcgen05 / TMEM / TMA), the building block of ImageEncoderViT's Linear layers ------------- */
 /* C = act(A[M,K] B[N,K]^T + bias) with fp16 (bf16 if is_bf16) operands and fp32 accumulation.  Exactly one of
  * out16 (fp16/bf16 [M,ldc]) / out32 (fp32 [M,ldc], optional fp32 residual added) is non-null.
- * precision 1: single pass.  2: A is carried as hi|lo halves, A = [M,2K] with lo at column K (B plain).
- * 3: B too (B = [N,2K]); products hi.hi + lo.hi + hi.lo accumulate in the same TMEM tile (~fp32 accuracy).
+ * precision 1: single pass.  2: the weights B are carried as fp16 hi|lo halves, B = [N,2K] with lo at column K (A plain):
+ * A.B_hi + A.B_lo.  3: A too (A = [M,2K]); products hi.hi + lo.hi + hi.lo accumulate in the same TMEM tile (~fp32).
  * split_off > 0 (out16 only): additionally writes lo = fp16(v - fp16(v)) at column offset split_off.
  * Replaces torch.nn.Linear inside segment_anything.modeling.image_encoder (un-vendored; call site
  * sam_pt/modeling/sam_pt.py:849 -> SamPredictor.set_image -> ImageEncoderViT.forward). */

@@ -360,11 +360,19 @@ def mask_decode(sd: SD, image_embeddings, image_pe, sparse, dense, multimask_out
     src = torch.repeat_interleave(image_embeddings, tokens.shape[0], dim=0) + dense
     pos_src = torch.repeat_interleave(image_pe, tokens.shape[0], dim=0)
     b, c, h, w = src.shape
+    if hq is not None:
+        hq = dict(hq)
+        hq["_pre_src"] = src
     hs, src = two_way_transformer(sd, p + "transformer.", src, pos_src, tokens)
     iou_token_out = hs[:, 0, :]
     ntok = n_mask_tok + (1 if hq is not None else 0)
     mask_tokens_out = hs[:, 1:1 + ntok, :]
     src = src.transpose(1, 2).view(b, c, h, w)
+    if hq is not None and hq.get("hf_upscale_quirk", False):
+        # transformers' sam_hq port up-scales the PRE-transformer embedding, spatially transposed
+        # (modeling_sam_hq.py: `image_embeddings.transpose(2, 3).reshape(...)` on the (B,C,H,W) input); upstream m43/sam-hq
+        # up-scales the transformer's output.  Only used to cross-check the remaining HQ pieces against HF.
+        src = hq["_pre_src"].transpose(2, 3).reshape(b, c, h, w)
     u = F.conv_transpose2d(src, sd[p + "output_upscaling.0.weight"], sd[p + "output_upscaling.0.bias"], stride=2)
     u = F.gelu(_ln2d(u, sd[p + "output_upscaling.1.weight"], sd[p + "output_upscaling.1.bias"]))
     u = F.gelu(F.conv_transpose2d(u, sd[p + "output_upscaling.3.weight"], sd[p + "output_upscaling.3.bias"], stride=2))

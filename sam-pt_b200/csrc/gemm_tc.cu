@@ -228,7 +228,7 @@ int gemm_tc(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int 
 using namespace sampt;
 
 // Unit-test / building-block entry: C = act(A B^T + bias), fp16 operands (bf16 if is_bf16), fp32 accumulation.
-// precision: 1 = single pass; 2 = A carried as hi|lo (A is [M, 2K], lo at column K); 3 = both A and B carried as hi|lo.
+// precision: 1 = single pass; 2 = B (weights) carried as hi|lo (B is [N, 2K], lo at column K), A plain; 3 = both carried as hi|lo.
 extern "C" int sampt_gemm_f16(sampt_ctx* ctx, const void* A, int lda, const void* B, int ldb, int M, int N, int K, int precision,
                               int is_bf16, const float* bias, int act, void* out16, float* out32, const float* resid, int ldc,
                               int split_off, void* stream) {
@@ -236,10 +236,15 @@ extern "C" int sampt_gemm_f16(sampt_ctx* ctx, const void* A, int lda, const void
   GemmSeg seg{};
   seg.nseg = precision;
   SAMPT_CHECK(precision >= 1 && precision <= 3, "precision must be 1, 2 or 3");
-  // segment order: hi.hi, lo.hi, hi.lo
-  seg.a_off[0] = 0; seg.b_off[0] = 0;
-  seg.a_off[1] = K; seg.b_off[1] = 0;
-  seg.a_off[2] = 0; seg.b_off[2] = K;
+  // precision 1: A.B ; 2: A.(B_hi + B_lo)  (weights carried as hi|lo) ; 3: A_hi.B_hi + A_lo.B_hi + A_hi.B_lo
+  if (precision == 2) {
+    seg.a_off[0] = 0; seg.b_off[0] = 0;
+    seg.a_off[1] = 0; seg.b_off[1] = K;
+  } else {
+    seg.a_off[0] = 0; seg.b_off[0] = 0;
+    seg.a_off[1] = K; seg.b_off[1] = 0;
+    seg.a_off[2] = 0; seg.b_off[2] = K;
+  }
   GemmEpi ep{};
   ep.out16 = reinterpret_cast<__half*>(out16);
   ep.out32 = out32;

@@ -13,8 +13,10 @@ int sgemm_nt_skip(Ctx* c, cudaStream_t st, const float* X, int ldx, const float*
 
 // ---- PIPS (pips_kernels.cu)
 struct PipsWin {
-  int N, S, stride, frame, T;
-  int fidx[8];             // real frame index feeding window slot s (handles tail padding and the flipped pass)
+  int N, S, stride, T;
+  const int* wp;           // device "window params": [0] = current frame f, [1] = n_missing, [2+s] = real frame index feeding
+                           // window slot s (tail padding / flipped pass).  In device memory so a captured CUDA graph of
+                           // one window can be replayed for every window of the clip.
   const float* pyr[4];     // pyramid level base pointers, each (T, H_l, W_l, 128) channels-last
   int H[4], W[4];
   float* coords;           // (N, S, 2) feature-map pixels
@@ -44,8 +46,7 @@ int mixer_token(Ctx* c, cudaStream_t st, float* x, float* xln, const uint8_t* ac
 int mixer_mean(Ctx* c, cudaStream_t st, const float* xln, float* xm, int N, int S, int D);
 int pips_update(Ctx* c, cudaStream_t st, const PipsWin& w, const float* delta, const float* gn_w, const float* gn_b,
                 const float* up_w, const float* up_b);
-int pips_link(Ctx* c, cudaStream_t st, const PipsWin& w, const float* vis_w, const float* vis_b, float thr0, int T,
-              int n_missing);
+int pips_link(Ctx* c, cudaStream_t st, const PipsWin& w, const float* vis_w, const float* vis_b, float thr0, int T);
 
 __global__ void conv7x7s2_u8_kernel(const uint8_t* frames, const float* w, const float* bias, float* out, int H, int W,
                                     int Ho, int Wo);

@@ -373,8 +373,9 @@ int avgpool2_nhwc(Ctx* c, cudaStream_t st, const float* in, float* out, int Nimg
 __global__ void pips_window_init_kernel(PipsWin w) {
   const int n = blockIdx.x, c = threadIdx.x;  // 128 threads
   if (!w.active[n]) return;
-  const float x = w.traj[((size_t)w.frame * w.N + n) * 2 + 0] / (float)w.stride;
-  const float y = w.traj[((size_t)w.frame * w.N + n) * 2 + 1] / (float)w.stride;
+  const int frame = w.wp[0];
+  const float x = w.traj[((size_t)frame * w.N + n) * 2 + 0] / (float)w.stride;
+  const float y = w.traj[((size_t)frame * w.N + n) * 2 + 1] / (float)w.stride;
   if (c < w.S) {
     w.coords[((size_t)n * w.S + c) * 2 + 0] = x;
     w.coords[((size_t)n * w.S + c) * 2 + 1] = y;
@@ -382,7 +383,7 @@ __global__ void pips_window_init_kernel(PipsWin w) {
   float f;
   if (w.sample_feat) {
     const int H = w.H[0], W = w.W[0];
-    const float* fm = w.pyr[0] + (size_t)w.fidx[0] * H * W * 128;
+    const float* fm = w.pyr[0] + (size_t)w.wp[2] * H * W * 128;
     float x0f = floorf(x), y0f = floorf(y);
     int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
     int x0c = min(max(x0, 0), W - 1), x1c = min(max(x1, 0), W - 1);
@@ -421,7 +422,7 @@ pips_corr_kernel(PipsWin w, float* __restrict__ xin, int ldx) {
   const float4 q = *reinterpret_cast<const float4*>(ff + lane * 4);
   const float cx0 = w.coords[((size_t)n * w.S + s) * 2 + 0];
   const float cy0 = w.coords[((size_t)n * w.S + s) * 2 + 1];
-  const int fi = w.fidx[s];
+  const int fi = w.wp[2 + s];
   // 4 levels x 64 pixels = 256 dots, 8 warps -> 32 dots per warp; all loads issued before the reductions (ILP)
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
@@ -501,7 +502,7 @@ pips_corr_only_kernel(PipsWin w, float* __restrict__ fcorr) {
   const float4 q = *reinterpret_cast<const float4*>(ff + lane * 4);
   const float cx0 = w.coords[((size_t)n * w.S + s) * 2 + 0];
   const float cy0 = w.coords[((size_t)n * w.S + s) * 2 + 1];
-  const int fi = w.fidx[s];
+  const int fi = w.wp[2 + s];
 #pragma unroll
   for (int l = 0; l < 4; ++l) {
     const int H = w.H[l], W = w.W[l];
@@ -715,11 +716,11 @@ int pips_update(Ctx* c, cudaStream_t st, const PipsWin& w, const float* delta, c
 // one thread per point (N is small); fully on device so the chain needs no per-point host logic.
 // =====================================================================================================
 __global__ void pips_link_kernel(PipsWin w, const float* __restrict__ vis_w, const float* __restrict__ vis_b, float thr0,
-                                 int T, int n_missing) {
+                                 int T) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= w.N) return;
   if (!w.active[n]) return;
-  const int f = w.frame, S = w.S;
+  const int f = w.wp[0], n_missing = w.wp[1], S = w.S;
   // vis logits for each window slot, sigmoid, write frames f+1 .. f+S-1-n_missing
   for (int s = 1; s < S - n_missing; ++s) {
     const float* ff = w.ffeats + ((size_t)n * S + s) * 128;
@@ -741,9 +742,8 @@ __global__ void pips_link_kernel(PipsWin w, const float* __restrict__ vis_w, con
   }
   w.cur[n] = nxt;
 }
-int pips_link(Ctx* c, cudaStream_t st, const PipsWin& w, const float* vis_w, const float* vis_b, float thr0, int T,
-              int n_missing) {
-  pips_link_kernel<<<cdiv(w.N, 64), 64, 0, st>>>(w, vis_w, vis_b, thr0, T, n_missing);
+int pips_link(Ctx* c, cudaStream_t st, const PipsWin& w, const float* vis_w, const float* vis_b, float thr0, int T) {
+  pips_link_kernel<<<cdiv(w.N, 64), 64, 0, st>>>(w, vis_w, vis_b, thr0, T);
   c->launches++;
   SAMPT_LAUNCH_CHECK();
   return 0;

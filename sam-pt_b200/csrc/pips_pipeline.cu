@@ -148,9 +148,9 @@ extern "C" int sampt_pips_pyramid(sampt_ctx* ctx, const float* fmaps, int T, int
 
 namespace sampt {
 
-__global__ void set_active_kernel(const int* __restrict__ v, int f, uint8_t* __restrict__ active, int N) {
+__global__ void set_active_kernel(const int* __restrict__ v, const int* __restrict__ wp, uint8_t* __restrict__ active, int N) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < N) active[n] = (v[n] == f) ? 1 : 0;
+  if (n < N) active[n] = (v[n] == wp[0]) ? 1 : 0;
 }
 __global__ void track_state_init_kernel(const float* __restrict__ q, float* traj, float* vis, int* start, int* cur, int T, int N,
                                         int flip) {
@@ -277,34 +277,74 @@ extern "C" int sampt_pips_track(sampt_ctx* ctx, const float* fmaps, const float*
     cur_h[n] = start_h[n];
   }
   int windows_done = 0;
-  for (int f = 0; f < T - 1; ++f) {
+  // per-window parameters live in device memory (w.wp) so that ONE captured CUDA graph of a window (~280 kernels:
+  // activity mask, state init, 6 x {corr lookup, 12-layer mixer, update}, vis head + linking) is replayed for every window
+  int* wp_d;
+  SAMPT_TRY(ws_get(c, &wp_d, 16, "window params"));
+  w.wp = wp_d;
+  int* wp_h = reinterpret_cast<int*>(reinterpret_cast<char*>(c->pinned) + (64 << 10));
+  static const bool use_graphs = []() { const char* e = getenv("SAMPT_PIPS_GRAPHS"); return !(e && e[0] == '0'); }();
+  cudaGraphExec_t exec = nullptr;
+  long long graph_launches = 0;
+  int rc_all = 0;
+  for (int f = 0; f < T - 1 && rc_all == 0; ++f) {
     if (max_windows > 0 && windows_done >= max_windows) break;
     bool any = false, born = false;
     for (int n = 0; n < N; ++n) { any |= (cur_h[n] == f); born |= (start_h[n] == f); }
     if (!any) continue;  // pips/tracker.py:69-70
     ++windows_done;
     const int n_missing = std::max(0, f + S - T);
-    w.frame = f;
+    wp_h[0] = f; wp_h[1] = n_missing;
     for (int s = 0; s < S; ++s) {
       int t = std::min(f + s, T - 1);  // tail padding repeats the last frame (pips/tracker.py:73-78)
-      w.fidx[s] = flip ? (T - 1 - t) : t;
+      wp_h[2 + s] = flip ? (T - 1 - t) : t;
     }
+    SAMPT_CUDA(cudaMemcpyAsync(wp_d, wp_h, 10 * sizeof(int), cudaMemcpyHostToDevice, st));
     if (born) {  // feature-init pass: only ffeat is consumed (pips/tracker.py:81-90; the 6 mixer iterations are dead)
-      set_active_kernel<<<cdiv(N, 64), 64, 0, st>>>(start_d, f, active_d, N);
+      set_active_kernel<<<cdiv(N, 64), 64, 0, st>>>(start_d, wp_d, active_d, N);
       c->launches++;
       w.sample_feat = 1;
       SAMPT_TRY(pips_window_init(c, st, w));
     }
-    set_active_kernel<<<cdiv(N, 64), 64, 0, st>>>(cur_d, f, active_d, N);
-    c->launches++;
     w.sample_feat = 0;
-    SAMPT_TRY(pips_window_init(c, st, w));
-    for (int it = 0; it < iters; ++it) SAMPT_TRY(pips_iteration(c, st, w, m, b));
-    SAMPT_TRY(pips_link(c, st, w, m.vis_w, m.vis_b, thr0, T, n_missing));
-    SAMPT_CUDA(cudaMemcpyAsync(cur_h, cur_d, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
-    SAMPT_CUDA(cudaStreamSynchronize(st));
+    auto enqueue_window = [&](cudaStream_t s2) -> int {
+      set_active_kernel<<<cdiv(N, 64), 64, 0, s2>>>(cur_d, wp_d, active_d, N);
+      c->launches++;
+      SAMPT_TRY(pips_window_init(c, s2, w));
+      for (int it = 0; it < iters; ++it) SAMPT_TRY(pips_iteration(c, s2, w, m, b));
+      SAMPT_TRY(pips_link(c, s2, w, m.vis_w, m.vis_b, thr0, T));
+      return 0;
+    };
+    if (!use_graphs) {
+      SAMPT_TRY(enqueue_window(st));
+    } else {
+      if (!exec) {
+        if (!c->cap_stream) SAMPT_CUDA(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+        SAMPT_CUDA(cudaStreamSynchronize(st));
+        const long long l0 = c->launches;
+        SAMPT_CUDA(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed));
+        int rc = enqueue_window(c->cap_stream);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
+        graph_launches = c->launches - l0;
+        c->launches = l0;
+        if (rc != 0) return rc;
+        SAMPT_CHECK(e == cudaSuccess && graph != nullptr, "stream capture of the PIPS window failed: %s", cudaGetErrorString(e));
+        SAMPT_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+      }
+      cudaError_t e = cudaGraphLaunch(exec, st);
+      if (e != cudaSuccess) { set_error("cudaGraphLaunch(PIPS window): %s", cudaGetErrorString(e)); rc_all = -1; break; }
+      c->launches += graph_launches;
+    }
+    if (cudaMemcpyAsync(cur_h, cur_d, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      set_error("PIPS window read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+      rc_all = -1;
+    }
   }
-  return 0;
+  if (exec) cudaGraphExecDestroy(exec);
+  return rc_all;
 }
 
 // Unit-test entry: fused correlation lookup alone (the "first kernel").
@@ -315,8 +355,15 @@ extern "C" int sampt_pips_corr_lookup(sampt_ctx* ctx, const float* fmaps, const 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   SAMPT_CHECK(S >= 1 && S <= 8, "S must be in [1,8]");
   PipsWin w{};
-  w.N = N; w.S = S; w.stride = 4; w.T = S; w.frame = 0;
-  for (int s = 0; s < S; ++s) w.fidx[s] = s;
+  w.N = N; w.S = S; w.stride = 4; w.T = S;
+  c->ws_reset();
+  int* wp_d;
+  SAMPT_TRY(ws_get(c, &wp_d, 16, "window params"));
+  int* wp_h = reinterpret_cast<int*>(reinterpret_cast<char*>(c->pinned) + (64 << 10));
+  wp_h[0] = 0; wp_h[1] = 0;
+  for (int s = 0; s < 8; ++s) wp_h[2 + s] = s;
+  SAMPT_CUDA(cudaMemcpyAsync(wp_d, wp_h, 10 * sizeof(int), cudaMemcpyHostToDevice, st));
+  w.wp = wp_d;
   w.pyr[0] = fmaps; w.pyr[1] = l1; w.pyr[2] = l2; w.pyr[3] = l3;
   w.H[0] = H4; w.W[0] = W4;
   for (int l = 1; l < 4; ++l) { w.H[l] = w.H[l - 1] / 2; w.W[l] = w.W[l - 1] / 2; }

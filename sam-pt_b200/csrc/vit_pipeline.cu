@@ -23,9 +23,14 @@ __global__ void window_map_kernel(int* __restrict__ map, int B, int G, int ws, i
 static GemmSeg make_seg(int precision, int K) {
   GemmSeg s{};
   s.nseg = precision;
-  s.a_off[0] = 0; s.b_off[0] = 0;   // hi.hi
-  s.a_off[1] = K; s.b_off[1] = 0;   // lo.hi
-  s.a_off[2] = 0; s.b_off[2] = K;   // hi.lo
+  if (precision == 2) {               // weights split only: A.(W_hi + W_lo)
+    s.a_off[0] = 0; s.b_off[0] = 0;
+    s.a_off[1] = 0; s.b_off[1] = K;
+  } else {
+    s.a_off[0] = 0; s.b_off[0] = 0;   // hi.hi
+    s.a_off[1] = K; s.b_off[1] = 0;   // lo.hi
+    s.a_off[2] = 0; s.b_off[2] = K;   // hi.lo
+  }
   return s;
 }
 
@@ -36,8 +41,8 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int H
   const int D = d.D, G = d.G, GG = G * G, HD = D / d.nheads, ws = d.window;
   const int nW = (G + ws - 1) / ws, Lw = ws * ws;
   const int Mtok = B * GG, Mwin = B * nW * nW * Lw;
-  const int asp = precision >= 2 ? 2 : 1;  // A operands carried as hi|lo
-  const int bsp = precision >= 3 ? 2 : 1;  // B operands (weights) carried as hi|lo
+  const int asp = precision >= 3 ? 2 : 1;  // A operands (activations) carried as hi|lo
+  const int bsp = precision >= 2 ? 2 : 1;  // B operands (weights) carried as hi|lo
   const int Kpe = 3 * d.P * d.P;
   const std::string p = "sam.image_encoder.";
   c->ws_reset();

@@ -62,22 +62,24 @@ def test_gemm_residual_and_split_output():
 
 @pytest.mark.parametrize("precision", [2, 3])
 def test_gemm_split_precision(precision):
-    """fp32 inputs carried as fp16 hi|lo: 3-pass reaches ~fp32 accuracy, 2-pass is exact in A only."""
+    """operands carried as fp16 hi|lo: 3 passes reach ~fp32 accuracy for fp32 A and B; 2 passes are exact in B (weights)
+    for fp16-representable A."""
     M, N, K = 640, 768, 512
     g = torch.Generator().manual_seed(3)
     A32 = torch.randn((M, K), generator=g)
     B32 = torch.randn((N, K), generator=g) / K ** 0.5
+    if precision == 2:
+        A32 = A32.half().float()  # activations are fp16 in this mode
 
     def split(x):
         hi = x.half()
         lo = (x - hi.float()).half()
         return torch.cat([hi, lo], dim=1).cuda()
 
-    A = split(A32)
-    B = split(B32) if precision == 3 else B32.half().cuda()
+    A = split(A32) if precision == 3 else A32.half().cuda()
+    B = split(B32)
     out = _run(A, B, M, N, K, precision=precision, out32=True)
-    Bref = B32 if precision == 3 else B32.half().float()
-    ref = A32.double() @ Bref.double().T
+    ref = A32.double() @ B32.double().T
     err = (out.cpu().double() - ref).abs().max().item()
     assert err < 5e-5, err
     # and it must be far better than the single-pass result

@@ -39,7 +39,7 @@ def test_pil_resize_gpu_bit_exact():
             assert np.array_equal(out[b].permute(1, 2, 0).cpu().numpy(), ref), (h, w)
 
 
-@pytest.mark.parametrize("vit,precision,tol", [("vit_test", 1, 6e-3), ("vit_test", 2, 3e-3), ("vit_test", 3, 2e-4),
+@pytest.mark.parametrize("vit,precision,tol", [("vit_test", 1, 6e-3), ("vit_test", 2, 4e-3), ("vit_test", 3, 2e-4),
                                                ("vit_test80", 1, 6e-3), ("vit_test80", 3, 2e-4)])
 def test_vit_encoder_matches_oracle(vit, precision, tol):
     """relative L2 error of the (B,256,64,64) embedding; batch of 2 frames exercises the frame batching."""
@@ -172,3 +172,33 @@ def test_precision_dial_report(tmp_path):
     with open(os.path.join(root, "gpurun_out", "precision_dial_c1.json"), "w") as fh:
         json.dump({"config": "C1 (2x240x320, ViT-B + PIPS, 4 pts), per-frame mask IoU vs CPU oracle", "iou_by_precision": report}, fh)
     assert min(report[3]) >= 0.999
+
+
+def test_sampt_c2_slice_vit_h(tmp_path):
+    """BASELINE config C2's model and resolution (SAM ViT-H + PIPS, 480x854, 8 points, 12 refinements) on the first 2 frames
+    of the C2 clip (the CPU oracle needs ~12 s per ViT-H frame): coords within 1e-3 px, per-frame IoU >= 0.999."""
+    cfg = sam_ref.VIT_H
+    sam_sd = _sam_sd(cfg, 7202)
+    pips_sd = synth.condition_pips(synth.make_state_dict(pips_ref.pips_state_dict_shapes(), 7201))
+    ckpt = synth.write_pips_checkpoint_dir(pips_sd, str(tmp_path / "pips"))
+    video = synth.make_video_dict(50, 480, 854, 8)
+    video["image"] = video["image"][:2]
+    ref = sampt_ref.sampt_forward(pips_sd, sam_ref.RefSamPredictor(sam_sd, cfg), video, positive_points_per_mask=8,
+                                  sam_iou_threshold=-1e9)
+    model = factory.build_sam_pt("vit_h", sam_sd, ckpt, positive_points_per_mask=8, sam_iou_threshold=-1e9)
+    out = model(video)
+    assert (out["trajectories"].cpu() - ref["trajectories"]).abs().max() < 1e-3
+    assert torch.equal(out["visibilities"].cpu(), ref["visibilities"])
+    ious = [_iou(out["logits"][0][f].cpu(), ref["logits"][0][f]) for f in range(2)]
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    rep = {"default_precision": model.sam_predictor.model.image_encoder.precision, "iou": ious}
+    for p in (1, 2):
+        model.sam_predictor.model.image_encoder.precision = p
+        o = model(video)
+        rep[f"iou_precision_{p}"] = [_iou(o["logits"][0][f].cpu(), ref["logits"][0][f]) for f in range(2)]
+    with open(os.path.join(root, "gpurun_out", "precision_dial_c2slice.json"), "w") as fh:
+        json.dump(rep, fh)
+    assert min(ious) >= 0.999, ious
