@@ -37,6 +37,9 @@ int sampt_ctx_create(int device, sampt_ctx** out);
 int sampt_ctx_destroy(sampt_ctx* ctx);
 /* caller-owned scratch slab that pipelines bump-allocate from (no cudaMalloc inside the library) */
 int sampt_ctx_set_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes);
+/* optional dedicated slab for sampt_vit_encode, so the encoder can run on its own stream concurrently with the PIPS and
+ * decode pipelines (which use the general workspace / decoder slab) */
+int sampt_ctx_set_vit_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes);
 /* optional second slab with STABLE addresses for the SAM decode chain: when set, sampt_sam_predict_refine captures one CUDA
  * graph per chain shape and replays it (one launch per frame instead of ~500).  Re-setting it drops the cached graphs
  * (must be called after decoder weights are re-registered). */
@@ -118,6 +121,14 @@ int sampt_sam_predict(sampt_ctx* ctx, const float* feat_tok, int G, const float*
 int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const float* coords, const int* labels, int K,
                              const float* pos_coords, const int* pos_labels, int n_pos_first, int n_refine, int in_h, int in_w,
                              int H, int W, float* logits, float* iou, float* low_res, int* n_refine_done, void* stream);
+
+/* HQ-SAM (segment_anything_hq.modeling.mask_decoder_hq.MaskDecoderHQ, un-vendored m43/sam-hq @ 75c73fa; config
+ * configs/model/sam/samhq_vit_huge.yaml:19-27).  sampt_sam_hq_features computes the per-frame
+ * `embedding_encoder(image_embeddings) + compress_vit_feat(interm_embeddings[0])` map ([16*G*G][32], channels-last);
+ * sampt_sam_set_hq_features selects it (NULL = plain SAM) for the following predict calls, whose single-mask output then
+ * is mask_sam + mask_hq (hq_token_only=False). */
+int sampt_sam_hq_features(sampt_ctx* ctx, const float* feat_tok, const float* interm_tok, int G, float* out, void* stream);
+int sampt_sam_set_hq_features(sampt_ctx* ctx, const float* hq_features);
 
 #ifdef __cplusplus
 }

@@ -73,11 +73,16 @@ struct Ctx {
   size_t dec_bytes = 0, dec_off = 0;
   cudaStream_t cap_stream = nullptr;
   std::map<std::vector<int>, void*> graph_cache;
+  const float* hq_feat = nullptr;  // HQ-SAM features of the current frame (decoder.cu), caller-owned
 
   const TensorRef* find(const std::string& name) const {
     auto it = tensors.find(name);
     return it == tensors.end() ? nullptr : &it->second;
   }
+  // optional dedicated slab for the ViT encoder so that it can run on its own stream concurrently with the PIPS / decode
+  // pipelines (which bump-allocate from the general workspace)
+  char* vit_base = nullptr;
+  size_t vit_bytes = 0;
   void ws_reset() { ws_off = 0; }
   void* ws_alloc(size_t bytes) {
     size_t a = (ws_off + 255) & ~size_t(255);

@@ -418,7 +418,7 @@ mlp3_kernel(Mlp3Jobs jobs, const int* skip) {
 __global__ void __launch_bounds__(256)
 upscale_mask_kernel(const float* __restrict__ u1, const float* __restrict__ lnw, const float* __restrict__ lnb,
                     const float* __restrict__ w2 /*[64][32][2][2]*/, const float* __restrict__ b2, const float* __restrict__ hyper,
-                    int n_masks, float* __restrict__ low_res, int G, const int* skip) {
+                    int n_masks, float* __restrict__ low_res, int G, float* __restrict__ u_out /*[R*R][32] or null*/, const int* skip) {
   SKIP_RETURN(skip);
   __shared__ float sw[64 * 32 * 4];
   __shared__ float sh[4 * 32];
@@ -454,9 +454,93 @@ upscale_mask_kernel(const float* __restrict__ u1, const float* __restrict__ lnw,
 #pragma unroll
     for (int ci = 0; ci < 64; ++ci) a = fmaf(v[ci], sw[(ci * 32 + co) * 4 + sub], a);
     a = gelu_erf(a);
+    if (u_out) u_out[(size_t)pix * 32 + co] = a;
     for (int m = 0; m < n_masks; ++m) outm[m] = fmaf(sh[m * 32 + co], a, outm[m]);
   }
   for (int m = 0; m < n_masks; ++m) low_res[(size_t)m * R * R + pix] = outm[m];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// HQ-SAM (MaskDecoderHQ of m43/sam-hq, un-vendored; SURVEY Appendix B.2 last paragraph)
+// ------------------------------------------------------------------------------------------------------------------
+// hq_features = embedding_encoder(image_embeddings) + compress_vit_feat(interm[0]); both are ConvT(k2,s2) -> LN2d -> GELU ->
+// ConvT(k2,s2) stacks: the first ConvT of each was produced by a GEMM as e1[tok][(dy*2+dx)*64 + c] / c1[tok][(dy*2+dx)*256 + c].
+// one thread per low-res (256x256) pixel, 32 output channels.
+__global__ void __launch_bounds__(256)
+hq_features_kernel(const float* __restrict__ e1, const float* __restrict__ c1, const float* __restrict__ e_lnw,
+                   const float* __restrict__ e_lnb, const float* __restrict__ e_w2 /*[64][32][2][2]*/, const float* __restrict__ e_b2,
+                   const float* __restrict__ c_lnw, const float* __restrict__ c_lnb, const float* __restrict__ c_w2 /*[256][32][2][2]*/,
+                   const float* __restrict__ c_b2, float* __restrict__ out /*[R*R][32]*/, int G) {
+  const int R = 4 * G;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= R * R) return;
+  const int Y = pix / R, X = pix % R;
+  const int y2 = Y >> 1, x2 = X >> 1, sub = (Y & 1) * 2 + (X & 1);
+  const int ty = y2 >> 1, tx = x2 >> 1, sub1 = (y2 & 1) * 2 + (x2 & 1);
+  float acc[32];
+#pragma unroll
+  for (int co = 0; co < 32; ++co) acc[co] = e_b2[co] + c_b2[co];
+  {  // embedding_encoder branch (64 channels)
+    const float* p = e1 + (size_t)(ty * G + tx) * 256 + sub1 * 64;
+    float s = 0.f;
+    for (int c = 0; c < 64; ++c) s += p[c];
+    float mean = s * (1.0f / 64.0f), sq = 0.f;
+    for (int c = 0; c < 64; ++c) { float d = p[c] - mean; sq += d * d; }
+    float rstd = 1.0f / sqrtf(sq * (1.0f / 64.0f) + 1e-6f);
+    for (int ci = 0; ci < 64; ++ci) {
+      float v = gelu_erf(e_lnw[ci] * ((p[ci] - mean) * rstd) + e_lnb[ci]);
+#pragma unroll
+      for (int co = 0; co < 32; ++co) acc[co] = fmaf(v, __ldg(e_w2 + (ci * 32 + co) * 4 + sub), acc[co]);
+    }
+  }
+  {  // compress_vit_feat branch (256 channels)
+    const float* p = c1 + (size_t)(ty * G + tx) * 1024 + sub1 * 256;
+    float s = 0.f;
+    for (int c = 0; c < 256; ++c) s += p[c];
+    float mean = s * (1.0f / 256.0f), sq = 0.f;
+    for (int c = 0; c < 256; ++c) { float d = p[c] - mean; sq += d * d; }
+    float rstd = 1.0f / sqrtf(sq * (1.0f / 256.0f) + 1e-6f);
+    for (int ci = 0; ci < 256; ++ci) {
+      float v = gelu_erf(c_lnw[ci] * ((p[ci] - mean) * rstd) + c_lnb[ci]);
+#pragma unroll
+      for (int co = 0; co < 32; ++co) acc[co] = fmaf(v, __ldg(c_w2 + (ci * 32 + co) * 4 + sub), acc[co]);
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 32; co += 4)
+    *reinterpret_cast<float4*>(out + (size_t)pix * 32 + co) = make_float4(acc[co], acc[co + 1], acc[co + 2], acc[co + 3]);
+}
+// LayerNorm2d(64) + GELU in place on a channels-last [pixels][64] map, one warp per pixel
+__global__ void __launch_bounds__(256)
+ln64_gelu_kernel(float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b, int npix, const int* skip) {
+  SKIP_RETURN(skip);
+  const int pix = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (pix >= npix) return;
+  float* p = x + (size_t)pix * 64;
+  float a = p[lane], c = p[lane + 32];
+  float mean = warp_sum(a + c) * (1.0f / 64.0f);
+  float da = a - mean, dc = c - mean;
+  float rstd = 1.0f / sqrtf(warp_sum(da * da + dc * dc) * (1.0f / 64.0f) + 1e-6f);
+  p[lane] = gelu_erf(g[lane] * (da * rstd) + b[lane]);
+  p[lane + 32] = gelu_erf(g[lane + 32] * (dc * rstd) + b[lane + 32]);
+}
+// low_res[pix] += hyper_hq . (maskfeature[pix] + hq_features[pix])      (mask = mask_sam + mask_hq, hq_token_only=False)
+__global__ void hq_mask_add_kernel(const float* __restrict__ mf, const float* __restrict__ hqf, const float* __restrict__ hyper_hq,
+                                   float* __restrict__ low_res, int npix, const int* skip) {
+  SKIP_RETURN(skip);
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  float a = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; c += 4) {
+    float4 u = *reinterpret_cast<const float4*>(mf + (size_t)pix * 32 + c);
+    float4 v = *reinterpret_cast<const float4*>(hqf + (size_t)pix * 32 + c);
+    a = fmaf(hyper_hq[c], u.x + v.x, a);
+    a = fmaf(hyper_hq[c + 1], u.y + v.y, a);
+    a = fmaf(hyper_hq[c + 2], u.z + v.z, a);
+    a = fmaf(hyper_hq[c + 3], u.w + v.w, a);
+  }
+  low_res[pix] += a;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -565,6 +649,13 @@ struct DecW {
   DenseW dense;
   PromptArgs prompt;
   int n_out_tok;
+  // HQ-SAM
+  int hq = 0;
+  Mlp3Job hq_mlp;
+  const float *mf0_w, *mf0_b, *mf_lnw, *mf_lnb, *mf3_w, *mf3_b;
+  const float *enc0_w, *enc0_b4, *enc_lnw, *enc_lnb, *enc3_w, *enc3_b;
+  const float *cv0_w, *cv0_b4, *cv_lnw, *cv_lnb, *cv3_w, *cv3_b;
+  int vit_dim = 0;
 };
 
 static int load_attn(Ctx* c, const std::string& p, AttnW* a, int internal) {
@@ -622,6 +713,21 @@ static int load_dec(Ctx* c, DecW* w) {
   const TensorRef* ot = c->find(md + "output_tokens");
   pa.n_out_tok = (int)ot->dims[0];
   w->n_out_tok = pa.n_out_tok;
+  w->hq = c->find(md + "hf_mlp.layers.0.weight") != nullptr;
+  if (w->hq) {
+    SAMPT_CHECK(pa.n_out_tok == 6, "HQ decoder expects 6 output tokens (iou, 4 mask, hq), got %d", pa.n_out_tok);
+    SAMPT_TRY(load_mlp3(c, md + "hf_mlp.", &w->hq_mlp, 32));
+    SAMPT_TRY(get_f32(c, md + "embedding_maskfeature.0.weight_rsck", &w->mf0_w)); SAMPT_TRY(get_f32(c, md + "embedding_maskfeature.0.bias", &w->mf0_b));
+    SAMPT_TRY(get_f32(c, md + "embedding_maskfeature.1.weight", &w->mf_lnw)); SAMPT_TRY(get_f32(c, md + "embedding_maskfeature.1.bias", &w->mf_lnb));
+    SAMPT_TRY(get_f32(c, md + "embedding_maskfeature.3.weight_rsck", &w->mf3_w)); SAMPT_TRY(get_f32(c, md + "embedding_maskfeature.3.bias", &w->mf3_b));
+    SAMPT_TRY(get_f32(c, md + "embedding_encoder.0.weight_gemm", &w->enc0_w)); SAMPT_TRY(get_f32(c, md + "embedding_encoder.0.bias4", &w->enc0_b4));
+    SAMPT_TRY(get_f32(c, md + "embedding_encoder.1.weight", &w->enc_lnw)); SAMPT_TRY(get_f32(c, md + "embedding_encoder.1.bias", &w->enc_lnb));
+    SAMPT_TRY(get_f32(c, md + "embedding_encoder.3.weight", &w->enc3_w)); SAMPT_TRY(get_f32(c, md + "embedding_encoder.3.bias", &w->enc3_b));
+    SAMPT_TRY(get_f32(c, md + "compress_vit_feat.0.weight_gemm", &w->cv0_w)); SAMPT_TRY(get_f32(c, md + "compress_vit_feat.0.bias4", &w->cv0_b4));
+    SAMPT_TRY(get_f32(c, md + "compress_vit_feat.1.weight", &w->cv_lnw)); SAMPT_TRY(get_f32(c, md + "compress_vit_feat.1.bias", &w->cv_lnb));
+    SAMPT_TRY(get_f32(c, md + "compress_vit_feat.3.weight", &w->cv3_w)); SAMPT_TRY(get_f32(c, md + "compress_vit_feat.3.bias", &w->cv3_b));
+    w->vit_dim = (int)c->find(md + "compress_vit_feat.0.weight_gemm")->dims[1];
+  }
   return 0;
 }
 
@@ -629,6 +735,7 @@ struct DecBufs {
   float *tokens, *queries, *qpe, *tq, *tk, *tv, *ta, *tmp, *mlp_h;   // token side  (T rows)
   float *src, *keys, *ik, *iv, *iq, *ia;                            // image side  (4096 rows)
   float *u1, *hyper, *iou4, *part;
+  float *u_sam, *mf1, *mf2;  // HQ only
   int T;
 };
 
@@ -723,6 +830,7 @@ struct DecodeCall {
   float* low_res;            // [n_masks, 256, 256]
   int* bbox;                 // [5] or null
   const int* skip;
+  const float* hq_feat;      // [256*256][32] HQ features of this frame, or null (plain SAM)
 };
 
 static int decode_once(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, const DecodeCall& d, int G) {
@@ -753,13 +861,32 @@ static int decode_once(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, const Decod
   jobs.j[d.n_masks] = w.iou;
   jobs.j[d.n_masks].x = b.queries;
   jobs.j[d.n_masks].y = b.iou4;
-  mlp3_kernel<<<d.n_masks + 1, 256, 0, st>>>(jobs, d.skip);
+  int njobs = d.n_masks + 1;
+  const bool hq = w.hq && d.hq_feat != nullptr;
+  if (hq) {
+    SAMPT_CHECK(d.n_masks == 1, "HQ decoder: only single-mask output (multimask_output=False) is built");
+    jobs.j[njobs] = w.hq_mlp;
+    jobs.j[njobs].x = b.queries + (size_t)5 * 256;  // hq token row
+    jobs.j[njobs].y = b.hyper + 4 * 32;
+    ++njobs;
+  }
+  mlp3_kernel<<<njobs, 256, 0, st>>>(jobs, d.skip);
   LAUNCH_OK();
   // upscaling: ConvT(256->64) as GEMM [GG,256] x [256(4 sub-pixels x 64), 256]^T, then fused LN+GELU+ConvT+GELU+hyper dot
   SAMPT_TRY(sg(c, st, b.keys, 256, w.up0_w, w.up0_b4, nullptr, 0, b.u1, 256, GG, 256, 256, 0, d.skip));
   upscale_mask_kernel<<<cdiv(16 * GG, 256), 256, 0, st>>>(b.u1, w.up_lnw, w.up_lnb, w.up3_w, w.up3_b, b.hyper, d.n_masks, d.low_res,
-                                                         G, d.skip);
+                                                         G, hq ? b.u_sam : nullptr, d.skip);
   LAUNCH_OK();
+  if (hq) {
+    // upscaled_embedding_hq = embedding_maskfeature(upscaled_embedding_sam) + hq_features ; mask += hyper_hq . that
+    const int R = 4 * G;
+    SAMPT_TRY(conv_nhwc_f32(c, st, b.u_sam, w.mf0_w, w.mf0_b, b.mf1, 1, R, R, 32, 64, 3, 3, 1, 1, d.skip));
+    ln64_gelu_kernel<<<cdiv(R * R, 8), 256, 0, st>>>(b.mf1, w.mf_lnw, w.mf_lnb, R * R, d.skip);
+    LAUNCH_OK();
+    SAMPT_TRY(conv_nhwc_f32(c, st, b.mf1, w.mf3_w, w.mf3_b, b.mf2, 1, R, R, 64, 32, 3, 3, 1, 1, d.skip));
+    hq_mask_add_kernel<<<cdiv(R * R, 256), 256, 0, st>>>(b.mf2, d.hq_feat, b.hyper + 4 * 32, d.low_res, R * R, d.skip);
+    LAUNCH_OK();
+  }
   postprocess_kernel<<<cdiv((long long)d.n_masks * d.H * d.W, 256), 256, 0, st>>>(d.low_res, d.n_masks, 4 * G, 16 * G, d.in_h, d.in_w,
                                                                                  d.H, d.W, d.logits, d.bbox, d.skip);
   LAUNCH_OK();
@@ -785,7 +912,10 @@ static int alloc_dec_bufs(Ctx* c, DecBufs* b, int Tmax, int GG) {
   SAMPT_TRY(ws_get(c, &b->iq, (size_t)GG * 128, "dec iq"));
   SAMPT_TRY(ws_get(c, &b->ia, (size_t)GG * 128, "dec ia"));
   SAMPT_TRY(ws_get(c, &b->u1, (size_t)GG * 256, "dec u1"));
-  SAMPT_TRY(ws_get(c, &b->hyper, (size_t)4 * 32, "dec hyper"));
+  SAMPT_TRY(ws_get(c, &b->hyper, (size_t)8 * 32, "dec hyper"));
+  SAMPT_TRY(ws_get(c, &b->u_sam, (size_t)16 * GG * 32, "dec u_sam"));
+  SAMPT_TRY(ws_get(c, &b->mf1, (size_t)16 * GG * 64, "dec mf1"));
+  SAMPT_TRY(ws_get(c, &b->mf2, (size_t)16 * GG * 32, "dec mf2"));
   SAMPT_TRY(ws_get(c, &b->iou4, (size_t)8, "dec iou"));
   SAMPT_TRY(ws_get(c, &b->part, (size_t)Tmax * 8 * ((GG + 255) / 256) * 18, "dec attn partials"));
   return 0;
@@ -819,6 +949,7 @@ extern "C" int sampt_sam_predict(sampt_ctx* ctx, const float* feat_tok, int G, c
   d.feat_tok = feat_tok; d.coords = coords; d.labels = labels; d.K = K; d.box = box; d.use_box = box ? 1 : 0;
   d.mask_in = mask_input; d.n_masks = multimask ? 3 : 1; d.tok0 = multimask ? 1 : 0;
   d.in_h = in_h; d.in_w = in_w; d.H = H; d.W = W; d.logits = logits; d.iou = iou; d.low_res = low_res; d.bbox = nullptr; d.skip = nullptr;
+  d.hq_feat = w.hq ? c->hq_feat : nullptr;
   return decode_once(c, st, w, b, d, G);
 }
 
@@ -833,6 +964,7 @@ struct RefineShape { int G, K, npos, nref, in_h, in_w, H, W; };
 struct RefinePtrs {
   const float* feat_tok; const float* coords; const int* labels; const float* pos_coords; const int* pos_labels;
   float* logits; float* iou; float* low_res; int* n_done; int* bbox; int* skip; float* box;
+  const float* hq_feat = nullptr;
 };
 
 // enqueue the whole predict_mask chain (sam_pt.py:781-828) on `st`
@@ -841,7 +973,7 @@ static int enqueue_refine_chain(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, co
   c->launches++;
   DecodeCall d{};
   d.feat_tok = p.feat_tok; d.n_masks = 1; d.tok0 = 0; d.in_h = s.in_h; d.in_w = s.in_w; d.H = s.H; d.W = s.W;
-  d.logits = p.logits; d.iou = p.iou; d.low_res = p.low_res; d.skip = nullptr;
+  d.logits = p.logits; d.iou = p.iou; d.low_res = p.low_res; d.skip = nullptr; d.hq_feat = p.hq_feat;
   if (s.npos > 0) {
     d.coords = p.pos_coords; d.labels = p.pos_labels; d.K = s.npos; d.box = nullptr; d.use_box = 0; d.mask_in = nullptr; d.bbox = nullptr;
     SAMPT_TRY(decode_once(c, st, w, b, d, s.G));
@@ -865,7 +997,7 @@ static int enqueue_refine_chain(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, co
 struct RefineGraph {
   RefineShape shape;
   DecBufs bufs;
-  float *feat, *coords, *pos_coords, *logits, *iou, *low, *box;
+  float *feat, *coords, *pos_coords, *logits, *iou, *low, *box, *hqfeat = nullptr;
   int *labels, *pos_labels, *n_done, *bbox, *skip;
   cudaGraphExec_t exec = nullptr;
   long long launches = 0;
@@ -884,7 +1016,7 @@ static int dec_get(Ctx* c, T** out, size_t count, const char* what) {
   return 0;
 }
 
-static int build_refine_graph(Ctx* c, DecW& w, const RefineShape& s, RefineGraph** out) {
+static int build_refine_graph(Ctx* c, DecW& w, const RefineShape& s, bool hq, RefineGraph** out) {
   RefineGraph* g = new RefineGraph();
   g->shape = s;
   const int GG = s.G * s.G, Tmax = w.n_out_tok + s.K + 2;
@@ -897,7 +1029,9 @@ static int build_refine_graph(Ctx* c, DecW& w, const RefineShape& s, RefineGraph
   SAMPT_TRY(dec_get(c, &b.src, (size_t)GG * 256, "src")); SAMPT_TRY(dec_get(c, &b.keys, (size_t)GG * 256, "keys"));
   SAMPT_TRY(dec_get(c, &b.ik, (size_t)GG * 128, "ik")); SAMPT_TRY(dec_get(c, &b.iv, (size_t)GG * 128, "iv"));
   SAMPT_TRY(dec_get(c, &b.iq, (size_t)GG * 128, "iq")); SAMPT_TRY(dec_get(c, &b.ia, (size_t)GG * 128, "ia"));
-  SAMPT_TRY(dec_get(c, &b.u1, (size_t)GG * 256, "u1")); SAMPT_TRY(dec_get(c, &b.hyper, (size_t)128, "hyper"));
+  SAMPT_TRY(dec_get(c, &b.u1, (size_t)GG * 256, "u1")); SAMPT_TRY(dec_get(c, &b.hyper, (size_t)256, "hyper"));
+  SAMPT_TRY(dec_get(c, &b.u_sam, (size_t)16 * GG * 32, "u_sam")); SAMPT_TRY(dec_get(c, &b.mf1, (size_t)16 * GG * 64, "mf1"));
+  SAMPT_TRY(dec_get(c, &b.mf2, (size_t)16 * GG * 32, "mf2"));
   SAMPT_TRY(dec_get(c, &b.iou4, (size_t)8, "iou4"));
   SAMPT_TRY(dec_get(c, &b.part, (size_t)Tmax * 8 * ((GG + 255) / 256) * 18, "attn partials"));
   SAMPT_TRY(dec_get(c, &g->feat, (size_t)GG * 256, "feat stage"));
@@ -909,6 +1043,11 @@ static int build_refine_graph(Ctx* c, DecW& w, const RefineShape& s, RefineGraph
   SAMPT_TRY(dec_get(c, &g->n_done, (size_t)8, "n_done")); SAMPT_TRY(dec_get(c, &g->bbox, (size_t)8, "bbox"));
   SAMPT_TRY(dec_get(c, &g->skip, (size_t)8, "skip")); SAMPT_TRY(dec_get(c, &g->box, (size_t)8, "box"));
   RefinePtrs p{g->feat, g->coords, g->labels, g->pos_coords, g->pos_labels, g->logits, g->iou, g->low, g->n_done, g->bbox, g->skip, g->box};
+  if (hq) {
+    SAMPT_TRY(dec_get(c, &g->hqfeat, (size_t)16 * GG * 32, "hq features stage"));
+    SAMPT_CUDA(cudaMemset(g->hqfeat, 0, (size_t)16 * GG * 32 * sizeof(float)));
+    p.hq_feat = g->hqfeat;
+  }
   if (!c->cap_stream) SAMPT_CUDA(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
   // eager warm-up on the capture stream (sets function attributes, touches every code path), then capture.
   // cap_stream does not synchronise with the legacy default stream: make sure pending weight uploads have landed.
@@ -970,15 +1109,17 @@ extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, i
     SAMPT_TRY(ws_get(c, &skip, 1, "skip"));
     SAMPT_TRY(ws_get(c, &box, 4, "box"));
     RefinePtrs p{feat_tok, coords, labels, pos_coords, pos_labels, logits, iou, low_res, n_refine_done, bbox, skip, box};
+    p.hq_feat = w.hq ? c->hq_feat : nullptr;
     return enqueue_refine_chain(c, st, w, b, s, p);
   }
-  std::vector<int> key{G, K, s.npos, n_refine, in_h, in_w, H, W, w.n_out_tok};
+  const bool hq = w.hq && c->hq_feat != nullptr;
+  std::vector<int> key{G, K, s.npos, n_refine, in_h, in_w, H, W, w.n_out_tok, hq ? 1 : 0};
   RefineGraph* g = nullptr;
   auto it = c->graph_cache.find(key);
   if (it == c->graph_cache.end()) {
     // weights may not change between capture and replay: the cache is dropped by sampt_ctx_set_decoder_workspace,
     // which the Python side calls whenever SAM's decoder weights are (re)registered
-    SAMPT_TRY(build_refine_graph(c, w, s, &g));
+    SAMPT_TRY(build_refine_graph(c, w, s, hq, &g));
     c->graph_cache[key] = g;
   } else {
     g = reinterpret_cast<RefineGraph*>(it->second);
@@ -991,11 +1132,40 @@ extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, i
     SAMPT_CUDA(cudaMemcpyAsync(g->pos_coords, pos_coords, (size_t)s.npos * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     SAMPT_CUDA(cudaMemcpyAsync(g->pos_labels, pos_labels, (size_t)s.npos * sizeof(int), cudaMemcpyDeviceToDevice, st));
   }
+  if (hq) SAMPT_CUDA(cudaMemcpyAsync(g->hqfeat, c->hq_feat, (size_t)16 * GG * 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   SAMPT_CUDA(cudaGraphLaunch(g->exec, st));
   c->launches += g->launches;
   SAMPT_CUDA(cudaMemcpyAsync(logits, g->logits, (size_t)H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
   SAMPT_CUDA(cudaMemcpyAsync(iou, g->iou, sizeof(float), cudaMemcpyDeviceToDevice, st));
   SAMPT_CUDA(cudaMemcpyAsync(low_res, g->low, (size_t)16 * GG * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (n_refine_done) SAMPT_CUDA(cudaMemcpyAsync(n_refine_done, g->n_done, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// HQ-SAM: per-frame `hq_features` = embedding_encoder(image_embeddings) + compress_vit_feat(interm_embeddings[0])
+// (MaskDecoderHQ.predict_masks prologue).  feat_tok [G*G,256], interm_tok [G*G,vit_dim] (output of the first global
+// attention block, token-major) -> out [16*G*G][32] channels-last low-res map.
+extern "C" int sampt_sam_hq_features(sampt_ctx* ctx, const float* feat_tok, const float* interm_tok, int G, float* out, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  c->ws_reset();
+  DecW w;
+  SAMPT_TRY(load_dec(c, &w));
+  SAMPT_CHECK(w.hq, "sampt_sam_hq_features: the registered mask decoder is not an HQ decoder");
+  const int GG = G * G;
+  float *e1, *c1;
+  SAMPT_TRY(ws_get(c, &e1, (size_t)GG * 256, "hq e1"));
+  SAMPT_TRY(ws_get(c, &c1, (size_t)GG * 1024, "hq c1"));
+  SAMPT_TRY(sgemm_nt(c, st, feat_tok, 256, w.enc0_w, 256, w.enc0_b4, nullptr, 0, e1, 256, GG, 256, 256, 0));
+  SAMPT_TRY(sgemm_nt(c, st, interm_tok, w.vit_dim, w.cv0_w, w.vit_dim, w.cv0_b4, nullptr, 0, c1, 1024, GG, 1024, w.vit_dim, 0));
+  hq_features_kernel<<<cdiv(16 * GG, 256), 256, 0, st>>>(e1, c1, w.enc_lnw, w.enc_lnb, w.enc3_w, w.enc3_b, w.cv_lnw, w.cv_lnb, w.cv3_w,
+                                                        w.cv3_b, out, G);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  return 0;
+}
+// Select the HQ features used by subsequent sampt_sam_predict / sampt_sam_predict_refine calls (NULL = plain SAM masks).
+extern "C" int sampt_sam_set_hq_features(sampt_ctx* ctx, const float* hq_features) {
+  reinterpret_cast<Ctx*>(ctx)->hq_feat = hq_features;
   return 0;
 }

@@ -55,7 +55,8 @@ template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_nhwc_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                      float* __restrict__ out, int Nimg, int H, int W, int Cin, int Ho, int Wo, int Cout, int R, int S,
-                     int stride, int pad) {
+                     int stride, int pad, const int* skip) {
+  if (skip != nullptr && *skip != 0) return;
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
   __shared__ __align__(16) float As[2][BK][BM + 4];
@@ -183,16 +184,16 @@ conv_nhwc_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, 
 }
 
 int conv_nhwc_f32(Ctx* c, cudaStream_t st, const float* in, const float* w, const float* bias, float* out, int Nimg,
-                  int H, int W, int Cin, int Cout, int R, int S, int stride, int pad) {
+                  int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, const int* skip) {
   SAMPT_CHECK(Cin % 16 == 0 && Cout % 4 == 0, "conv_nhwc_f32: Cin %% 16 and Cout %% 4 required (Cin=%d Cout=%d)", Cin, Cout);
   int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
   long long M = (long long)Nimg * Ho * Wo;
   if (Cout % 64 == 0 || Cout >= 96) {
     dim3 grid(cdiv(Cout, 64), cdiv(M, 128));
-    conv_nhwc_f32_kernel<128, 64, 8, 4><<<grid, 256, 0, st>>>(in, w, bias, out, Nimg, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad);
+    conv_nhwc_f32_kernel<128, 64, 8, 4><<<grid, 256, 0, st>>>(in, w, bias, out, Nimg, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad, skip);
   } else {
     dim3 grid(cdiv(Cout, 32), cdiv(M, 128));
-    conv_nhwc_f32_kernel<128, 32, 8, 4><<<grid, 128, 0, st>>>(in, w, bias, out, Nimg, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad);
+    conv_nhwc_f32_kernel<128, 32, 8, 4><<<grid, 128, 0, st>>>(in, w, bias, out, Nimg, H, W, Cin, Ho, Wo, Cout, R, S, stride, pad, skip);
   }
   c->launches++;
   SAMPT_LAUNCH_CHECK();

@@ -45,7 +45,15 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int H
   const int bsp = precision >= 2 ? 2 : 1;  // B operands (weights) carried as hi|lo
   const int Kpe = 3 * d.P * d.P;
   const std::string p = "sam.image_encoder.";
-  c->ws_reset();
+  // the encoder allocates from its own slab when one is registered (stream-level overlap with PIPS / decode)
+  struct SlabGuard {
+    Ctx* c; char* b; size_t n, o; bool on;
+    SlabGuard(Ctx* c_) : c(c_), b(c_->ws_base), n(c_->ws_bytes), o(c_->ws_off), on(c_->vit_base != nullptr) {
+      if (on) { c->ws_base = c->vit_base; c->ws_bytes = c->vit_bytes; }
+      c->ws_off = 0;
+    }
+    ~SlabGuard() { if (on) { c->ws_base = b; c->ws_bytes = n; c->ws_off = o; } }
+  } slab_guard(c);
 
   float* x;           SAMPT_TRY(ws_get(c, &x, (size_t)Mtok * D, "vit x"));
   __half* A;          SAMPT_TRY(ws_get(c, &A, (size_t)std::max(Mwin, Mtok) * std::max(D, Kpe) * asp, "vit A"));
@@ -180,6 +188,13 @@ extern "C" int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B
   VitDims d{depth, embed_dim, num_heads, window_size, img_size / patch_size, patch_size, out_chans};
   return vit_forward(c, reinterpret_cast<cudaStream_t>(stream), resized_u8, B, Hr, Wr, d, global_idx_host, n_global, precision,
                      pixel_mean_host, pixel_std_host, features, interm);
+}
+
+extern "C" int sampt_ctx_set_vit_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  c->vit_base = reinterpret_cast<char*>(dev_ptr);
+  c->vit_bytes = bytes;
+  return 0;
 }
 
 extern "C" int sampt_pil_resize_u8(sampt_ctx* ctx, const uint8_t* in, int B, int H, int W, int Ho, int Wo, const int* hbounds,

@@ -27,17 +27,23 @@ def build_sam(vit: str = "vit_b", sam_state_dict: Optional[Dict[str, torch.Tenso
     from segment_anything.modeling.prompt_encoder import PromptEncoder
     from segment_anything.modeling.transformer import TwoWayTransformer
 
-    if hq:
-        raise NotImplementedError("HQ-SAM decoder is not built yet (SURVEY §8 row a19)")
     c = VIT_CFGS[vit]
+    if hq:
+        from sam_pt.modeling.sam import SamHQHydra
+        from segment_anything_hq.modeling.image_encoder import ImageEncoderViT
+        from segment_anything_hq.modeling.mask_decoder_hq import MaskDecoderHQ
     enc = ImageEncoderViT(depth=c["depth"], embed_dim=c["embed_dim"], img_size=1024, mlp_ratio=4,
                           norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_heads=c["num_heads"], patch_size=16,
                           qkv_bias=True, use_rel_pos=True, global_attn_indexes=c["global_attn_indexes"], window_size=14,
                           out_chans=256)
     pe = PromptEncoder(embed_dim=256, image_embedding_size=(64, 64), input_image_size=(1024, 1024), mask_in_chans=16)
-    md = MaskDecoder(num_multimask_outputs=3, transformer=TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8),
-                     transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256)
-    sam = SamHydra(image_encoder=enc, prompt_encoder=pe, mask_decoder=md, pixel_mean=[123.675, 116.28, 103.53],
+    tw = TwoWayTransformer(depth=2, embedding_dim=256, mlp_dim=2048, num_heads=8)
+    if hq:
+        md = MaskDecoderHQ(num_multimask_outputs=3, transformer=tw, transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256,
+                           vit_dim=c["embed_dim"])
+    else:
+        md = MaskDecoder(num_multimask_outputs=3, transformer=tw, transformer_dim=256, iou_head_depth=3, iou_head_hidden_dim=256)
+    sam = (SamHQHydra if hq else SamHydra)(image_encoder=enc, prompt_encoder=pe, mask_decoder=md, pixel_mean=[123.675, 116.28, 103.53],
                    pixel_std=[58.395, 57.12, 57.375], checkpoint=None, prompt_embed_dim=256, image_size=1024, vit_patch_size=16,
                    image_embedding_size=64)
     if sam_state_dict is not None:
@@ -48,14 +54,17 @@ def build_sam(vit: str = "vit_b", sam_state_dict: Optional[Dict[str, torch.Tenso
 
 
 def build_sam_pt(vit: str, sam_state_dict, pips_ckpt_dir: str, positive_points_per_mask: int, negative_points_per_mask: int = 0,
-                 iterative_refinement_iterations: int = 12, sam_iou_threshold: float = 0.7, device="cuda"):
+                 iterative_refinement_iterations: int = 12, sam_iou_threshold: float = 0.7, device="cuda", hq: bool = False):
     """configs/model/sam_pt.yaml with `model/point_tracker=pips`, `model/sam@...=sam_vit_*` and the demo-style overrides
     positive_points_per_mask=P negative_points_per_mask=0 (demo/demo.py:107-110)."""
     from sam_pt.modeling.sam_pt import SamPt
     from sam_pt.point_tracker.pips import PipsPointTracker
-    from segment_anything.predictor import SamPredictor
+    if hq:
+        from segment_anything_hq.predictor import SamPredictor
+    else:
+        from segment_anything.predictor import SamPredictor
 
-    sam = build_sam(vit, sam_state_dict)
+    sam = build_sam(vit, sam_state_dict, hq=hq)
     tracker = PipsPointTracker(checkpoint_path=pips_ckpt_dir, stride=4, s=8, initial_next_frame_visibility_threshold=0.9)
     model = SamPt(point_tracker=tracker, sam_predictor=SamPredictor(sam_model=sam), sam_iou_threshold=sam_iou_threshold,
                   positive_point_selection_method="kmedoids", negative_point_selection_method="mixed",

@@ -74,6 +74,14 @@ class Context:
         self._dec_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         check(lib().sampt_ctx_set_decoder_workspace(self._h, ptr(self._dec_ws), c_size_t(nbytes)), "set_decoder_workspace")
 
+    def ensure_vit_workspace(self, nbytes: int) -> None:
+        """Dedicated slab of the ViT encoder (lets it overlap with PIPS / decode on another stream)."""
+        cur = getattr(self, "_vit_ws", None)
+        if cur is None or cur.numel() < nbytes:
+            torch.cuda.synchronize(self.device)  # nothing may still be running out of the old slab
+            self._vit_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            check(lib().sampt_ctx_set_vit_workspace(self._h, ptr(self._vit_ws), c_size_t(nbytes)), "set_vit_workspace")
+
     def ensure_workspace(self, nbytes: int) -> None:
         if self._ws is None or self._ws.numel() < nbytes:
             self.set_workspace(nbytes)

@@ -111,7 +111,7 @@ class ImageEncoderViT(nn.Module):
         ctx = self.native_context()
         B, _, Hr, Wr = resized.shape
         g = self.img_size // self.patch_size
-        ctx.ensure_workspace(self.workspace_bytes(B))
+        ctx.ensure_vit_workspace(self.workspace_bytes(B))
         feats = torch.empty((B, self.out_chans, g, g), device=resized.device, dtype=torch.float32)
         interm = torch.empty((B, g, g, self.embed_dim), device=resized.device, dtype=torch.float32) if want_interm else None
         gidx = (c_int * max(1, len(self.global_attn_indexes)))(*self.global_attn_indexes)

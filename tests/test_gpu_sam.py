@@ -202,3 +202,55 @@ def test_sampt_c2_slice_vit_h(tmp_path):
     with open(os.path.join(root, "gpurun_out", "precision_dial_c2slice.json"), "w") as fh:
         json.dump(rep, fh)
     assert min(ious) >= 0.999, ious
+
+
+# ---------------------------------------------------------------------------------------------------------------- HQ-SAM
+@pytest.fixture(scope="module")
+def hq_setup():
+    from segment_anything_hq.predictor import SamPredictor
+    cfg = sam_ref.VIT_TEST
+    sd = synth.condition_sam(synth.make_state_dict(sam_ref.sam_state_dict_shapes(cfg, hq=True), 43))
+    sam = factory.build_sam("vit_test", sd, hq=True).cuda()
+    pred = SamPredictor(sam)
+    g = torch.Generator().manual_seed(19)
+    feats = torch.randn((1, 256, 64, 64), generator=g)
+    interm = torch.randn((1, 64, 64, cfg.embed_dim), generator=g)
+    ref = sam_ref.RefSamPredictor(sd, cfg, hq=True)
+    ref.features, ref.interm = feats, [interm]
+    ref.original_size, ref.input_size = (480, 854), (576, 1024)
+    pred.set_frames_features((480, 854), (feats.cuda(), interm.cuda()))
+    return sd, pred, ref, g
+
+
+@pytest.mark.parametrize("with_mask,with_box", [(False, False), (True, True)])
+def test_hq_predict_torch_matches_oracle(hq_setup, with_mask, with_box):
+    """MaskDecoderHQ single-mask output = SAM mask + HQ mask (hq_token_only=False), against the oracle restatement."""
+    sd, pred, ref, g = hq_setup
+    pts = torch.rand((1, 6, 2), generator=g) * torch.tensor([1000.0, 560.0])
+    labels = torch.tensor([[1, 1, 0, 1, 1, 1]], dtype=torch.int)
+    mask_in = torch.randn((1, 1, 256, 256), generator=g) if with_mask else None
+    box = torch.tensor([[[100.0, 150.0, 700.0, 440.0]]]) if with_box else None
+    rm, ri, rl = ref.predict_torch(pts, labels, box[:, 0] if with_box else None, mask_in, False, True)
+    cu = lambda t: t.cuda() if t is not None else None
+    m, i, l = pred.predict_torch(cu(pts), cu(labels), cu(box), cu(mask_in), False, True)
+    scale = max(1.0, rl.abs().max().item())
+    assert (l.cpu() - rl).abs().max() < 3e-4 * scale
+    assert (m.cpu() - rm).abs().max() < 3e-4 * scale
+    assert (i.cpu() - ri).abs().max() < 1e-4
+
+
+def test_hq_encoder_interm_and_e2e(tmp_path):
+    """HQ-SAM + PIPS end to end on a tiny clip (encoder returns the first global block's output; decoder adds the HQ mask)."""
+    from segment_anything_hq.predictor import SamPredictor
+    cfg = sam_ref.VIT_TEST
+    sam_sd = synth.condition_sam(synth.make_state_dict(sam_ref.sam_state_dict_shapes(cfg, hq=True), 47))
+    pips_sd = synth.condition_pips(synth.make_state_dict(pips_ref.pips_state_dict_shapes(), 7201))
+    ckpt = synth.write_pips_checkpoint_dir(pips_sd, str(tmp_path / "pips"))
+    video = synth.make_video_dict(3, 96, 128, 4)
+    ref = sampt_ref.sampt_forward(pips_sd, sam_ref.RefSamPredictor(sam_sd, cfg, hq=True), video, positive_points_per_mask=4,
+                                  sam_iou_threshold=-1e9)
+    model = factory.build_sam_pt("vit_test", sam_sd, ckpt, positive_points_per_mask=4, sam_iou_threshold=-1e9, hq=True)
+    out = model(video)
+    assert (out["trajectories"].cpu() - ref["trajectories"]).abs().max() < 1e-3
+    for f in range(3):
+        assert _iou(out["logits"][0][f].cpu(), ref["logits"][0][f]) >= 0.999, f

@@ -45,3 +45,24 @@ def test_vit_huge_override_composes():
     assert (enc["depth"], enc["embed_dim"], enc["num_heads"]) == (32, 1280, 16)
     assert enc["global_attn_indexes"] == [7, 15, 23, 31]
     assert cfg["sam_predictor"]["sam_model"]["checkpoint"] == "/x/models/sam_ckpts/sam_vit_h_4b8939.pth"
+
+
+def test_default_hq_config_instantiates(tmp_path):
+    """configs/model/sam_pt.yaml's own defaults select HQ-SAM ViT-H + `segment_anything_hq.predictor.SamPredictor`
+    (sam_pt.yaml:3-8); only the tracker group is switched to PIPS (CoTracker is not built yet)."""
+    from oracle import pips_ref
+    from sampt_b200 import hydra_lite, synth
+    pips_sd = synth.condition_pips(synth.make_state_dict(pips_ref.pips_state_dict_shapes(), 1))
+    synth.write_pips_checkpoint_dir(pips_sd, str(tmp_path / "models" / "pips_ckpts" / "reference_model"))
+    cfg = hydra_lite.compose_model(REF_CFG, {"point_tracker": "pips", "sam_predictor.sam_model.checkpoint": None,
+                                             # keep the unit test small: shrink the ViT, everything else as configured
+                                             "sam_predictor.sam_model.image_encoder.depth": 2,
+                                             "sam_predictor.sam_model.image_encoder.global_attn_indexes": [1]}, cwd=str(tmp_path))
+    assert cfg["sam_predictor"]["_target_"] == "segment_anything_hq.predictor.SamPredictor"
+    assert cfg["sam_predictor"]["sam_model"]["_target_"] == "sam_pt.modeling.sam.SamHQHydra"
+    assert cfg["sam_predictor"]["sam_model"]["mask_decoder"]["_target_"] == "segment_anything_hq.modeling.mask_decoder_hq.MaskDecoderHQ"
+    assert cfg["sam_predictor"]["sam_model"]["mask_decoder"]["vit_dim"] == 1280  # ${..image_encoder.embed_dim}
+    model = hydra_lite.instantiate(cfg)
+    import segment_anything_hq.predictor as hp
+    assert type(model.sam_predictor) is hp.SamPredictor
+    assert "mask_decoder.hf_token.weight" in model.sam_predictor.model.state_dict()
