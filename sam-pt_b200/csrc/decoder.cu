@@ -390,23 +390,25 @@ mlp3_kernel(Mlp3Jobs jobs, const int* skip) {
   SKIP_RETURN(skip);
   const Mlp3Job& J = jobs.j[blockIdx.x];
   __shared__ float a[256], b[256];
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   a[t] = J.x[t];
   __syncthreads();
-  float s = J.b0[t];
-  for (int k = 0; k < 256; ++k) s = fmaf(J.w0[t * 256 + k], a[k], s);
-  b[t] = fmaxf(s, 0.f);
+  // each warp produces outputs warp, warp+8, ...: the 256-long weight row is read coalesced (8 floats per lane)
+  auto layer = [&](const float* __restrict__ w, const float* __restrict__ bias, const float* in, float* out, int nout, bool relu) {
+    for (int o = warp; o < nout; o += 8) {
+      const float* wr = w + (size_t)o * 256;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(wr[lane + 32 * i], in[lane + 32 * i], s);
+      s = warp_sum(s);
+      if (lane == 0) { s += bias[o]; out[o] = relu ? fmaxf(s, 0.f) : s; }
+    }
+  };
+  layer(J.w0, J.b0, a, b, 256, true);
   __syncthreads();
-  s = J.b1[t];
-  for (int k = 0; k < 256; ++k) s = fmaf(J.w1[t * 256 + k], b[k], s);
+  layer(J.w1, J.b1, b, a, 256, true);
   __syncthreads();
-  a[t] = fmaxf(s, 0.f);
-  __syncthreads();
-  if (t < J.n_out) {
-    s = J.b2[t];
-    for (int k = 0; k < 256; ++k) s = fmaf(J.w2[t * 256 + k], a[k], s);
-    J.y[t] = s;
-  }
+  layer(J.w2, J.b2, a, J.y, J.n_out, false);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -176,6 +176,70 @@ sgemm_smallm_kernel(const float* __restrict__ X, int ldx, const float* __restric
   }
 }
 
+// M <= 64 rows (PIPS mixer: N*S = 64 rows for 8 points): register-tiled so that shared-memory traffic does not bound it.
+// CTA = 8 warps = 4 row groups (16 rows) x 2 column groups (8 columns) -> 64 x 16 outputs; lanes split K (float4 per
+// lane per step, X staged in smem in chunks of 128, W read coalesced straight from global/L1); per k-step a lane does
+// 16 LDS.128 + 8 LDG.128 for 512 FMAs; a shuffle tree finishes the 128 dot products of the warp.
+__global__ void __launch_bounds__(256)
+sgemm_m64_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                 const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
+  if (skip != nullptr && *skip != 0) return;
+  constexpr int KC = 128;
+  __shared__ __align__(16) float xs[64][KC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mg = warp & 3, cg = warp >> 2;
+  const int nbase = blockIdx.x * 16 + cg * 8;
+  float acc[16][8];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * (KC / 4); i += 256) {
+      int m = i / (KC / 4), c = (i % (KC / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && k0 + c < K) v = *reinterpret_cast<const float4*>(X + (size_t)m * ldx + k0 + c);
+      *reinterpret_cast<float4*>(&xs[m][c]) = v;
+    }
+    __syncthreads();
+    const int kk = k0 + lane * 4;
+    float4 w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      w[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nbase + j < N && kk < K) w[j] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(nbase + j) * ldw + kk));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 x = *reinterpret_cast<const float4*>(&xs[mg * 16 + i][lane * 4]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[i][j] = fmaf(x.x, w[j].x, acc[i][j]);
+        acc[i][j] = fmaf(x.y, w[j].y, acc[i][j]);
+        acc[i][j] = fmaf(x.z, w[j].z, acc[i][j]);
+        acc[i][j] = fmaf(x.w, w[j].w, acc[i][j]);
+      }
+    }
+  }
+  // reduce over lanes: after the tree, lane l holds output (i, j) with i*8 + j == l (mod 32) for i*8+j in [32r, 32r+32)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = warp_sum(acc[i][j]);
+      const int m = mg * 16 + i, n = nbase + j;
+      if (lane == ((i * 8 + j) & 31) && m < M && n < N) {
+        if (bias) v += bias[n];
+        if (act == 1) v = gelu_erf(v);
+        else if (act == 2) v = fmaxf(v, 0.f);
+        if (residual) v += residual[(size_t)m * ldr + n];
+        Y[(size_t)m * ldy + n] = v;
+      }
+    }
+  }
+}
+
 int sgemm_nt(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
              const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act) {
   return sgemm_nt_skip(c, st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, nullptr);
@@ -190,7 +254,7 @@ int sgemm_nt_skip(Ctx* c, cudaStream_t st, const float* X, int ldx, const float*
   } else if (M <= 32) {
     sgemm_smallm_kernel<32><<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   } else if (M <= 64) {
-    sgemm_smallm_kernel<64><<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+    sgemm_m64_kernel<<<cdiv(N, 16), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   } else {
     // tile choice: the largest tile that still yields ~a wave of CTAs on 148 SMs
     const long long t128 = (long long)cdiv(M, 128) * cdiv(N, 64), t64 = (long long)cdiv(M, 64) * cdiv(N, 64);

@@ -180,106 +180,154 @@ __global__ void __launch_bounds__(256)
 attn_prep_kernel(const __half* __restrict__ qkv, int ldq, const float* __restrict__ relh, const float* __restrict__ relw,
                  __half* __restrict__ Qx, __half* __restrict__ Kx, __half* __restrict__ Vt, int S, int L, int Lkp, int DK,
                  int D, int nheads, float scale, int TC) {
-  extern __shared__ float sm[];
+  // shared memory: q (half, padded rows), v (half, padded rows), one rel-pos table (fp32), extended Q columns (half)
+  constexpr int QP = HD + 8;  // row pitch in halves (16 B aligned, breaks the 160 B bank pattern)
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int EXT = DK - HD;
+  __half* sq = reinterpret_cast<__half*>(smraw);              // [TC][QP]
+  __half* sv = sq + (size_t)TC * QP;                          // [TC][QP]
+  __half* qext = sv + (size_t)TC * QP;                        // [TC][EXT]
+  float* sr = reinterpret_cast<float*>(qext + (size_t)TC * EXT);  // [2S-1][HD+1]
   const int chunk = blockIdx.x, h = blockIdx.y, wb = blockIdx.z;
   const int t0 = chunk * TC;
   const int nt = min(TC, L - t0);
-  float* sq = sm;                       // [TC][HD+1]
-  float* sr = sq + TC * (HD + 1);       // rel-pos rows: [2S-1][HD+1] (reused for h then w)
   const int tid = threadIdx.x;
   const size_t bh = (size_t)wb * nheads + h;
-  // load q (unscaled, fp32) ; write K' dot part, V^T, Q' scaled part
-  for (int i = tid; i < TC * HD; i += 256) {
-    int t = i / HD, d = i % HD;
-    float qv = 0.f;
+  constexpr int SEG = HD / 8;  // 16-byte segments per head row
+  // ---- phase 1: coalesced 16 B loads of q / k / v head rows; K' (dot part) and scaled Q' are written straight back
+  for (int i = tid; i < TC * SEG; i += 256) {
+    const int t = i / SEG, sgm = i % SEG;
+    uint4 qv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
     if (t < nt) {
-      const __half* rowp = qkv + (size_t)(wb * L + t0 + t) * ldq + h * HD;
-      qv = __half2float(rowp[d]);
-      float kv = __half2float(rowp[D + d]);
-      Qx[(bh * L + t0 + t) * DK + d] = __float2half_rn(qv * scale);
-      Kx[(bh * L + t0 + t) * DK + d] = __float2half_rn(kv);
+      const __half* rowp = qkv + (size_t)(wb * L + t0 + t) * ldq + h * HD + sgm * 8;
+      qv = *reinterpret_cast<const uint4*>(rowp);
+      const uint4 kv = *reinterpret_cast<const uint4*>(rowp + D);
+      vv = *reinterpret_cast<const uint4*>(rowp + 2 * D);
+      *reinterpret_cast<uint4*>(Kx + (bh * L + t0 + t) * DK + sgm * 8) = kv;
+      __half2* q2 = reinterpret_cast<__half2*>(&qv);
+      uint4 qs;
+      __half2* o2 = reinterpret_cast<__half2*>(&qs);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(q2[j]);
+        o2[j] = __floats2half2_rn(f.x * scale, f.y * scale);
+      }
+      *reinterpret_cast<uint4*>(Qx + (bh * L + t0 + t) * DK + sgm * 8) = qs;
     }
-    sq[t * (HD + 1) + d] = qv;
+    *reinterpret_cast<uint4*>(sq + (size_t)t * QP + sgm * 8) = qv;
+    *reinterpret_cast<uint4*>(sv + (size_t)t * QP + sgm * 8) = vv;
   }
-  // V^T: coalesce over t
-  for (int i = tid; i < TC * HD; i += 256) {
-    int d = i / TC, t = i % TC;
-    if (t < nt) Vt[(bh * HD + d) * Lkp + t0 + t] = qkv[(size_t)(wb * L + t0 + t) * ldq + 2 * D + h * HD + d];
-  }
-  // zero the tile padding of V^T (keys in [L, Lkp)) once per (bh): done by chunk 0
-  if (chunk == 0) {
-    for (int i = tid; i < HD * (Lkp - L); i += 256) {
-      int d = i / (Lkp - L), t = L + i % (Lkp - L);
-      Vt[(bh * HD + d) * Lkp + t] = __float2half_rn(0.f);
-    }
-  }
-  // one-hots and zero padding of the extended dims
-  for (int i = tid; i < TC * (DK - HD); i += 256) {
-    int t = i / (DK - HD), e = i % (DK - HD);
+  // K' extended columns: one-hots of (ky, kx) + zero padding, 16 B at a time
+  for (int i = tid; i < TC * (EXT / 8); i += 256) {
+    const int t = i / (EXT / 8), e0 = (i % (EXT / 8)) * 8;
     if (t < nt) {
-      int tt = t0 + t, ty = tt / S, tx = tt % S;
-      float kv = (e < S) ? (e == ty ? 1.f : 0.f) : (e < 2 * S ? ((e - S) == tx ? 1.f : 0.f) : 0.f);
-      Kx[(bh * L + tt) * DK + HD + e] = __float2half_rn(kv);
-      if (e >= 2 * S) Qx[(bh * L + tt) * DK + HD + e] = __float2half_rn(0.f);
+      const int tt = t0 + t, ty = tt / S, tx = tt % S;
+      __half hv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = e0 + j;
+        hv[j] = __float2half_rn((e == ty || e == S + tx) ? 1.f : 0.f);
+      }
+      *reinterpret_cast<uint4*>(Kx + (bh * L + tt) * DK + HD + e0) = *reinterpret_cast<uint4*>(hv);
     }
   }
-  // rel_h(q, j) = q . Rh[ty - j + S-1] ; rel_w(q, j) = q . Rw[tx - j + S-1]
+  // zero the unused tail of the extended Q columns
+  for (int i = tid; i < TC * (EXT - 2 * S); i += 256) {
+    const int t = i / (EXT - 2 * S), e = 2 * S + i % (EXT - 2 * S);
+    qext[(size_t)t * EXT + e] = __float2half_rn(0.f);
+  }
+  __syncthreads();
+  // V^T: thread = (d, group of 8 consecutive tokens) -> one 16 B store
+  {
+    const int ngrp = (TC + 7) / 8;
+    for (int i = tid; i < HD * ngrp; i += 256) {
+      const int g = i / HD, d = i % HD;  // consecutive threads -> consecutive d: conflict-free shared-memory reads
+      __half hv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int t = g * 8 + j;
+        hv[j] = (t < nt) ? sv[(size_t)t * QP + d] : __float2half_rn(0.f);
+      }
+      if (t0 + g * 8 < Lkp) *reinterpret_cast<uint4*>(Vt + (bh * HD + d) * Lkp + t0 + g * 8) = *reinterpret_cast<uint4*>(hv);
+    }
+    // the tile padding of V^T (keys in [L, Lkp)) beyond the last written group: zeros, written by the last chunk
+    if (t0 + TC >= L) {
+      const int first = ((L - t0 + 7) / 8) * 8 + t0;  // first key not covered by the groups above
+      for (int i = tid; i < HD * max(0, Lkp - first); i += 256) {
+        const int d = i / (Lkp - first), t = first + i % (Lkp - first);
+        Vt[(bh * HD + d) * Lkp + t] = __float2half_rn(0.f);
+      }
+    }
+  }
+  // ---- phase 2: rel_h(q, j) = q . Rh[ty - j + S-1] ; rel_w(q, j) = q . Rw[tx - j + S-1]   (4x4 register tiles)
   for (int pass = 0; pass < 2; ++pass) {
     const float* R = pass == 0 ? relh : relw;
     __syncthreads();
     for (int i = tid; i < (2 * S - 1) * HD; i += 256) sr[(i / HD) * (HD + 1) + (i % HD)] = R[i];
     __syncthreads();
-    // tiles of 4 tokens x 4 offsets
     const int ntile_t = (TC + 3) / 4, ntile_j = (S + 3) / 4;
     for (int tile = tid; tile < ntile_t * ntile_j; tile += 256) {
-      int tb = (tile / ntile_j) * 4, jb = (tile % ntile_j) * 4;
+      const int tb = (tile / ntile_j) * 4, jb = (tile % ntile_j) * 4;
       float acc[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
       int ridx[4][4];
+      const __half* qrow[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        int tt = t0 + min(tb + a, TC - 1);
-        int pos = pass == 0 ? (tt / S) : (tt % S);
+        const int tl = min(tb + a, TC - 1);
+        qrow[a] = sq + (size_t)tl * QP;
+        const int tt = t0 + tl;
+        const int pos = pass == 0 ? (tt / S) : (tt % S);
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          int j = min(jb + b, S - 1);
-          ridx[a][b] = (pos - j + S - 1) * (HD + 1);
+          const int j = min(jb + b, S - 1);
+          ridx[a][b] = min(max(pos - j + S - 1, 0), 2 * S - 2) * (HD + 1);
         }
       }
-      for (int d = 0; d < HD; ++d) {
-        float qv[4];
+      for (int d = 0; d < HD; d += 2) {
+        float2 qv[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) qv[a] = sq[min(tb + a, TC - 1) * (HD + 1) + d];
+        for (int a = 0; a < 4; ++a) qv[a] = __half22float2(*reinterpret_cast<const __half2*>(qrow[a] + d));
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(qv[a], sr[ridx[a][b] + d], acc[a][b]);
+          for (int b = 0; b < 4; ++b) {
+            acc[a][b] = fmaf(qv[a].x, sr[ridx[a][b] + d], acc[a][b]);
+            acc[a][b] = fmaf(qv[a].y, sr[ridx[a][b] + d + 1], acc[a][b]);
+          }
       }
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        int t = tb + a;
-        if (t >= nt) continue;
+        const int t = tb + a;
+        if (t >= TC) continue;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          int j = jb + b;
-          if (j >= S) continue;
-          Qx[(bh * L + t0 + t) * DK + HD + pass * S + j] = __float2half_rn(acc[a][b]);
+          const int j = jb + b;
+          if (j < S) qext[(size_t)t * EXT + pass * S + j] = __float2half_rn(acc[a][b]);
         }
       }
     }
+  }
+  __syncthreads();
+  // extended Q columns -> global, 16 B at a time
+  for (int i = tid; i < TC * (EXT / 8); i += 256) {
+    const int t = i / (EXT / 8), e0 = (i % (EXT / 8)) * 8;
+    if (t < nt) *reinterpret_cast<uint4*>(Qx + (bh * L + t0 + t) * DK + HD + e0) = *reinterpret_cast<const uint4*>(qext + (size_t)t * EXT + e0);
   }
 }
 int attn_prep(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* relh, const float* relw, __half* Qx, __half* Kx,
               __half* Vt, int nwb, int nheads, int S, int Lkp, int DK, int D, int HD, float scale) {
   const int L = S * S;
-  const int TC = (S == 14) ? 196 : 64;
+  const int TC = (S == 14) ? 200 : 64;  // one whole 14x14 window (padded to a multiple of 8) or one row of the 64x64 grid
   SAMPT_CHECK(HD == 80 || HD == 64, "attn_prep: head_dim %d not built (80 = ViT-H, 64 = ViT-B/L/test)", HD);
-  SAMPT_CHECK(DK >= HD + 2 * S, "attn_prep: DK too small");
+  SAMPT_CHECK(DK >= HD + 2 * S && (DK - HD) % 8 == 0 && Lkp % 8 == 0 && Lkp >= L, "attn_prep: unsupported sizes (S=%d DK=%d Lkp=%d)", S, DK, Lkp);
+  SAMPT_CHECK(D % 8 == 0 && ldq % 8 == 0, "attn_prep: D and ldq must be multiples of 8");
   dim3 grid(cdiv(L, TC), nheads, nwb);
-  size_t smem = ((size_t)TC * (HD + 1) + (size_t)(2 * S - 1) * (HD + 1)) * sizeof(float);
+  const int EXT = DK - HD;
+  size_t smem = (size_t)TC * (HD + 8) * 2 * 2 + (size_t)TC * EXT * 2 + (size_t)(2 * S - 1) * (HD + 1) * sizeof(float);
   if (HD == 80) {
     static bool set80 = false;
     if (!set80) { SAMPT_CUDA(cudaFuncSetAttribute(attn_prep_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set80 = true; }

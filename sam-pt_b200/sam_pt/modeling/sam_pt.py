@@ -8,6 +8,7 @@ contract and output dict.  The per-frame work is re-organised for the GPU:
 * one device->host copy per clip (trajectories + visibilities, a few KB) replaces the per-frame copies; the host then
   prepares every frame's prompt exactly as `prepare_points` does (sam_pt.py:726-758).
 """
+import os
 from typing import Optional
 
 import numpy as np
@@ -48,6 +49,10 @@ class SamPt(nn.Module):
         self.reinit_horizon = reinit_horizon
         self.reinit_variant = reinit_variant
         self.encoder_batch = 8          # frames per ViT launch
+        # run the ViT encoder (tensor pipe) on its own stream, concurrently with the PIPS tracker and the mask decoder
+        # (fp32 CUDA-core pipes, latency bound): the two halves of the path do not depend on each other until decode
+        self.overlap_streams = os.environ.get("SAMPT_OVERLAP", "1") != "0"
+        self._enc_stream = None
         self.outputs_on_cpu = False     # reference returns CPU tensors; keeping them on the device avoids a 82 MB copy
         self.frame_annotations = []
 
@@ -98,10 +103,35 @@ class SamPt(nn.Module):
                 "trajectories": trajectories, "visibilities": visibilities}
 
     def _forward(self, images, query_points):
+        pre = self._start_encoder(images) if self.overlap_streams else None
         trajectories, visibilities = self._track_points(images, query_points)
-        _, logits, scores_per_frame = self._apply_sam_to_trajectories(images, trajectories, visibilities)
+        _, logits, scores_per_frame = self._apply_sam_to_trajectories(images, trajectories, visibilities, pre=pre)
         scores = scores_per_frame.mean(dim=0)
         return trajectories, visibilities, logits, scores, scores_per_frame
+
+    @torch.no_grad()
+    def _start_encoder(self, images):
+        """Enqueue the SAM image encoder for every chunk of `images` on the encoder stream; returns per-chunk
+        (features, event) so the decode loop on the main stream can wait for exactly the chunk it needs."""
+        pred = self.sam_predictor
+        main = torch.cuda.current_stream()
+        if self._enc_stream is None:
+            pred.model.native_context()  # weight registration happens on the main stream, once
+            self._enc_stream = torch.cuda.Stream(device=self.device)
+        es = self._enc_stream
+        es.wait_stream(main)  # the uploaded frames
+        B = max(1, int(self.encoder_batch))
+        want_interm = pred._uses_interm()
+        out = []
+        with torch.cuda.stream(es):
+            for f0 in range(0, images.shape[0], B):
+                enc = pred.encode_frames(images[f0:f0 + B], want_interm=want_interm)
+                ev = torch.cuda.Event()
+                ev.record(es)
+                for t in (enc if isinstance(enc, tuple) else (enc,)):
+                    t.record_stream(main)
+                out.append((enc, ev))
+        return out
 
     # ------------------------------------------------------------------------------------------------ tracking
     def _track_points(self, rgbs, query_points):
@@ -127,17 +157,17 @@ class SamPt(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ SAM
     @torch.no_grad()
-    def _apply_sam_to_trajectories(self, images, trajectories, visibilities):
+    def _apply_sam_to_trajectories(self, images, trajectories, visibilities, pre=None):
         """reference sam_pt.py:694-866.  images (T,3,H,W) uint8 on the device."""
         n_frames = images.shape[0]
-        logits, scores_pf, counted = self._apply_sam_to_frames(images, list(range(n_frames)), trajectories, visibilities)
+        logits, scores_pf, counted = self._apply_sam_to_frames(images, list(range(n_frames)), trajectories, visibilities, pre=pre)
         counted_d = counted.to(self.device)
         cnt = counted_d.sum(dim=0).clamp(min=1)
         pred_scores = torch.where(counted_d, scores_pf, torch.zeros_like(scores_pf)).sum(dim=0) / cnt
         return pred_scores, logits, scores_pf
 
     @torch.no_grad()
-    def _apply_sam_to_frames(self, images, frame_ids, trajectories, visibilities):
+    def _apply_sam_to_frames(self, images, frame_ids, trajectories, visibilities, pre=None):
         """SAM on a subset of frames: images (n,3,H,W) uint8 on the device are the frames `frame_ids` of the clip whose
         full-clip trajectories (T,M,P,2) / visibilities (T,M,P) are given.  Returns logits (M,n,H,W), scores (n,M) on the
         device and `counted` (n,M) bool on the host (frames with at least one visible point)."""
@@ -174,9 +204,13 @@ class SamPt(nn.Module):
         n_ref = int(self.iterative_refinement_iterations) if self.iterative_refinement_iterations else 0
         B = max(1, int(self.encoder_batch))
         want_interm = pred._uses_interm()
-        for f0 in range(0, n_sub, B):
+        for ci, f0 in enumerate(range(0, n_sub, B)):
             chunk = images[f0:f0 + B]
-            enc = pred.encode_frames(chunk, want_interm=want_interm)
+            if pre is not None:  # encoder output produced on the encoder stream (see _start_encoder)
+                enc, ev = pre[ci]
+                torch.cuda.current_stream().wait_event(ev)
+            else:
+                enc = pred.encode_frames(chunk, want_interm=want_interm)
             feats, interm = enc if want_interm else (enc, None)
             for j in range(chunk.shape[0]):
                 i = f0 + j
@@ -221,6 +255,8 @@ class SamPt(nn.Module):
         for v in videos:
             fr = torch.stack([v["image"][f].to(dev, non_blocking=True) for f in own], dim=0)
             own_frames.append(fr)
+        pres = [self._start_encoder(fr) if self.overlap_streams else None for fr in own_frames]
+        for fr in own_frames:
             local_fm.append(trk.model.fnet_frames(fr))
         local = torch.stack(local_fm, dim=1)  # (n_own, C, H4, W4, 128): frame-major so one collective serves all clips
         # B. the exchange step
@@ -258,7 +294,7 @@ class SamPt(nn.Module):
             out_code = float(PointVisibilityType.OUTSIDE_FRAME.value)
             oob = (traj[..., 0] / w < 0.01) | (traj[..., 1] / h < 0.01) | (traj[..., 0] / w > 0.99) | (traj[..., 1] / h > 0.99)
             vis = torch.where(oob, torch.full_like(vis, out_code), vis)
-            logits, spf, _ = self._apply_sam_to_frames(own_frames[c], own, traj, vis)
+            logits, spf, _ = self._apply_sam_to_frames(own_frames[c], own, traj, vis, pre=pres[c])
             res = {"trajectories": traj, "visibilities": vis, "logits": logits, "frame_ids": own, "scores_per_frame": spf}
             if gather_logits:
                 res["logits"] = sharding.allgather_frames(logits.transpose(0, 1).contiguous(), T).transpose(0, 1)
