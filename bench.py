@@ -212,6 +212,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": roof,
+            "roofline_corr_gather": corr_roofline(dev),
             "cpu_baseline": cpu_base,
         }
         if breakdown:
@@ -352,6 +353,46 @@ def stage_breakdown(model, frames_dev, q_dev):
     out["sam_decode_13calls_per_frame"] = ms / 5
     out["sam_decode_clip_estimate"] = ms / 5 * T
     return {k: round(v, 3) for k, v in out.items()}
+
+
+def corr_roofline(dev, n_points=292):
+    """Secondary roofline entry: the fused PIPS correlation gather (pips_corr lookup) at a large point count
+    (C5-like: 256 queries + 36 support points), where it is bandwidth- rather than latency-bound.  Algorithmic bytes =
+    N * S * L * 64 px * 128 ch * 4 B = N x 1 MiB per launch (minimal formulation)."""
+    from ctypes import c_int
+    from sampt_b200 import native
+    S, H4, W4 = 8, 120, 213
+    g = torch.Generator(device="cpu").manual_seed(0)
+    lv = [torch.randn((S, H4 >> l, W4 >> l, 128), generator=g).to(dev) for l in range(4)]
+    ff = torch.randn((n_points, S, 128), generator=g).to(dev)
+    cc = (torch.rand((n_points, S, 2), generator=g) * torch.tensor([W4 - 1.0, H4 - 1.0])).to(dev)
+    out = torch.empty((n_points, S, 196), device=dev)
+    ctx = native.get_context(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def run():
+        native.check(native.lib().sampt_pips_corr_lookup(ctx.handle, native.ptr(lv[0]), native.ptr(lv[1]), native.ptr(lv[2]),
+                                                         native.ptr(lv[3]), c_int(S), c_int(H4), c_int(W4), native.ptr(ff),
+                                                         native.ptr(cc), c_int(n_points), native.ptr(out), native.stream_ptr()))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    times = []
+    for i in range(10):
+        flush.fill_(i)  # evict the pyramid from L2 so the gather is served by HBM
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sorted(times)[len(times) // 2]
+    nbytes = n_points * S * 4 * 64 * 128 * 4 + n_points * S * 196 * 4
+    pk = _peaks()
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "pips_corr_only_kernel (fused correlation gather, N=%d points)" % n_points, "achieved": gbs,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None, "ms": ms,
+            "peak_source": pk["src"], "algorithmic_bytes": nbytes, "l2": "flushed before every launch"}
 
 
 def gemm_roofline(model, dev, args):

@@ -30,6 +30,7 @@ extern "C" int sampt_ctx_create(int device, sampt_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   c->pinned_bytes = 1 << 20;
   SAMPT_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
+  SAMPT_TRY(sgemm_init());
   *out = reinterpret_cast<sampt_ctx*>(c);
   return 0;
 }

@@ -8,6 +8,7 @@ namespace sampt {
 int sgemm_nt(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
              const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act);
 
+int sgemm_init();
 int sgemm_nt_skip(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
                   const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip);
 

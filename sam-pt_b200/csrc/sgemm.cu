@@ -140,6 +140,10 @@ sgemm_smallm_kernel(const float* __restrict__ X, int ldx, const float* __restric
 #pragma unroll
   for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
   for (int k0 = 0; k0 < K; k0 += KC) {
+    // the weight row does not depend on the staged X tile: issue its load first so both latencies overlap
+    const int kk = k0 + lane * 4;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N && kk < K) w = __ldg(reinterpret_cast<const float4*>(W + (size_t)n * ldw + kk));
     __syncthreads();
     for (int i = threadIdx.x; i < MAXM * (KC / 4); i += 256) {
       int m = i / (KC / 4), c = (i % (KC / 4)) * 4;
@@ -149,9 +153,6 @@ sgemm_smallm_kernel(const float* __restrict__ X, int ldx, const float* __restric
     }
     __syncthreads();
     if (n < N) {
-      const int kk = k0 + lane * 4;
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kk < K) w = *reinterpret_cast<const float4*>(W + (size_t)n * ldw + kk);
 #pragma unroll
       for (int m = 0; m < MAXM; ++m) {
         float4 x = *reinterpret_cast<const float4*>(&xs[m][lane * 4]);
@@ -176,68 +177,125 @@ sgemm_smallm_kernel(const float* __restrict__ X, int ldx, const float* __restric
   }
 }
 
-// M <= 64 rows (PIPS mixer: N*S = 64 rows for 8 points): register-tiled so that shared-memory traffic does not bound it.
-// CTA = 8 warps = 4 row groups (16 rows) x 2 column groups (8 columns) -> 64 x 16 outputs; lanes split K (float4 per
-// lane per step, X staged in smem in chunks of 128, W read coalesced straight from global/L1); per k-step a lane does
-// 16 LDS.128 + 8 LDG.128 for 512 FMAs; a shuffle tree finishes the 128 dot products of the warp.
+// cp.async multi-stage FP32 GEMM.  The shapes on this path (PIPS mixer: 64 rows; mask decoder: 4096 x {128,256} outputs
+// with K = 128..2048) launch only ~30-250 CTAs, i.e. at most one or two per SM, so a kernel that loads a k-tile, waits,
+// computes, waits again is bound by global-memory LATENCY (measured: 15-60 us for 0.1-0.3 GFLOP).  Here every thread keeps
+// STAGES-1 k-tiles (BK = 32) in flight with cp.async (16 B, zero-fill on the K / M / N tails), and the shared-memory tiles
+// are k-contiguous with a 36-float pitch + strided row ownership (row = ty + 16*i) so that the float4 operand reads are
+// bank-conflict free.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <int BM, int BN, int TM, int TN, int STAGES>
 __global__ void __launch_bounds__(256)
-sgemm_m64_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
-                 const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
+sgemm_pipe_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                  const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
   if (skip != nullptr && *skip != 0) return;
-  constexpr int KC = 128;
-  __shared__ __align__(16) float xs[64][KC];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mg = warp & 3, cg = warp >> 2;
-  const int nbase = blockIdx.x * 16 + cg * 8;
-  float acc[16][8];
-#pragma unroll
-  for (int i = 0; i < 16; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += KC) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * (KC / 4); i += 256) {
-      int m = i / (KC / 4), c = (i % (KC / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M && k0 + c < K) v = *reinterpret_cast<const float4*>(X + (size_t)m * ldx + k0 + c);
-      *reinterpret_cast<float4*>(&xs[m][c]) = v;
-    }
-    __syncthreads();
-    const int kk = k0 + lane * 4;
-    float4 w[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      w[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (nbase + j < N && kk < K) w[j] = __ldg(reinterpret_cast<const float4*>(W + (size_t)(nbase + j) * ldw + kk));
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4 x = *reinterpret_cast<const float4*>(&xs[mg * 16 + i][lane * 4]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[i][j] = fmaf(x.x, w[j].x, acc[i][j]);
-        acc[i][j] = fmaf(x.y, w[j].y, acc[i][j]);
-        acc[i][j] = fmaf(x.z, w[j].z, acc[i][j]);
-        acc[i][j] = fmaf(x.w, w[j].w, acc[i][j]);
+  constexpr int BK = 32, PITCH = BK + 4;
+  static_assert(BM / TM == 16 && BN / TN == 16, "16x16 thread layout");
+  extern __shared__ __align__(16) float smem_f[];
+  float* As = smem_f;                               // [STAGES][BM][PITCH]
+  float* Bs = smem_f + (size_t)STAGES * BM * PITCH;  // [STAGES][BN][PITCH]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nk = (K + BK - 1) / BK;
+
+  auto issue = [&](int kt) {
+    if (kt < nk) {
+      const int st = kt % STAGES, k0 = kt * BK;
+      float* as = As + (size_t)st * BM * PITCH;
+      float* bs = Bs + (size_t)st * BN * PITCH;
+      for (int i = tid; i < BM * (BK / 4); i += 256) {
+        const int r = i / (BK / 4), c = (i % (BK / 4)) * 4;
+        const bool ok = (m0 + r < M) && (k0 + c < K);
+        cp_async16(as + r * PITCH + c, ok ? (X + (size_t)(m0 + r) * ldx + k0 + c) : X, ok);
+      }
+      for (int i = tid; i < BN * (BK / 4); i += 256) {
+        const int r = i / (BK / 4), c = (i % (BK / 4)) * 4;
+        const bool ok = (n0 + r < N) && (k0 + c < K);
+        cp_async16(bs + r * PITCH + c, ok ? (W + (size_t)(n0 + r) * ldw + k0 + c) : W, ok);
       }
     }
-  }
-  // reduce over lanes: after the tree, lane l holds output (i, j) with i*8 + j == l (mod 32) for i*8+j in [32r, 32r+32)
+    cp_async_commit();
+  };
+
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = warp_sum(acc[i][j]);
-      const int m = mg * 16 + i, n = nbase + j;
-      if (lane == ((i * 8 + j) & 31) && m < M && n < N) {
-        if (bias) v += bias[n];
-        if (act == 1) v = gelu_erf(v);
-        else if (act == 2) v = fmaxf(v, 0.f);
-        if (residual) v += residual[(size_t)m * ldr + n];
-        Y[(size_t)m * ldy + n] = v;
-      }
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue(s);
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(kt + STAGES - 1);  // refills the stage consumed in the previous iteration
+    const float* as = As + (size_t)(kt % STAGES) * BM * PITCH;
+    const float* bs = Bs + (size_t)(kt % STAGES) * BN * PITCH;
+#pragma unroll
+    for (int k = 0; k < BK; k += 4) {
+      float4 a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(as + (ty + 16 * i) * PITCH + k);
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(bs + (tx + 16 * j) * PITCH + k);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+        }
     }
   }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty + 16 * i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx + 16 * j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      if (act == 1) v = gelu_erf(v);
+      else if (act == 2) v = fmaxf(v, 0.f);
+      if (residual) v += residual[(size_t)gm * ldr + gn];
+      Y[(size_t)gm * ldy + gn] = v;
+    }
+  }
+}
+
+template <int BM, int BN, int TM, int TN, int STAGES>
+static int launch_pipe(cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias, const float* residual,
+                       int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
+  constexpr size_t smem = (size_t)STAGES * (BM + BN) * 36 * sizeof(float);
+  static bool set = false;
+  if (!set) {
+    SAMPT_CUDA(cudaFuncSetAttribute(sgemm_pipe_kernel<BM, BN, TM, TN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = true;
+  }
+  dim3 grid(cdiv(N, BN), cdiv(M, BM));
+  sgemm_pipe_kernel<BM, BN, TM, TN, STAGES><<<grid, 256, smem, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+  return 0;
+}
+
+// set the dynamic shared-memory attributes once, outside of any stream capture (called from sampt_ctx_create)
+int sgemm_init() {
+  SAMPT_CUDA(cudaFuncSetAttribute(sgemm_pipe_kernel<64, 16, 4, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (64 + 16) * 36 * 4));
+  SAMPT_CUDA(cudaFuncSetAttribute(sgemm_pipe_kernel<64, 64, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (64 + 64) * 36 * 4));
+  SAMPT_CUDA(cudaFuncSetAttribute(sgemm_pipe_kernel<128, 64, 8, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (128 + 64) * 36 * 4));
+  return 0;
 }
 
 int sgemm_nt(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
@@ -254,19 +312,16 @@ int sgemm_nt_skip(Ctx* c, cudaStream_t st, const float* X, int ldx, const float*
   } else if (M <= 32) {
     sgemm_smallm_kernel<32><<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   } else if (M <= 64) {
-    sgemm_m64_kernel<<<cdiv(N, 16), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+    SAMPT_TRY((launch_pipe<64, 16, 4, 1, 4>(st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip)));
   } else {
-    // tile choice: the largest tile that still yields ~a wave of CTAs on 148 SMs
+    // tile choice: the largest tile that still yields enough CTAs for 148 SMs
     const long long t128 = (long long)cdiv(M, 128) * cdiv(N, 64), t64 = (long long)cdiv(M, 64) * cdiv(N, 64);
-    if (t128 >= c->num_sms) {
-      dim3 grid(cdiv(N, 64), cdiv(M, 128));
-      sgemm_nt_kernel<128, 64, 16, 8, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+    if (t128 >= 2 * c->num_sms) {
+      SAMPT_TRY((launch_pipe<128, 64, 8, 4, 3>(st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip)));
     } else if (t64 >= c->num_sms / 2) {
-      dim3 grid(cdiv(N, 64), cdiv(M, 64));
-      sgemm_nt_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+      SAMPT_TRY((launch_pipe<64, 64, 4, 4, 4>(st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip)));
     } else {
-      dim3 grid(cdiv(N, 32), cdiv(M, 32));
-      sgemm_nt_kernel<32, 32, 16, 4, 4><<<grid, 64, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
+      SAMPT_TRY((launch_pipe<64, 16, 4, 1, 4>(st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip)));
     }
   }
   c->launches++;

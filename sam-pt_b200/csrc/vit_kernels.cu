@@ -187,7 +187,7 @@ attn_prep_kernel(const __half* __restrict__ qkv, int ldq, const float* __restric
   __half* sq = reinterpret_cast<__half*>(smraw);              // [TC][QP]
   __half* sv = sq + (size_t)TC * QP;                          // [TC][QP]
   __half* qext = sv + (size_t)TC * QP;                        // [TC][EXT]
-  float* sr = reinterpret_cast<float*>(qext + (size_t)TC * EXT);  // [2S-1][HD+1]
+  float* sr = reinterpret_cast<float*>(qext + (size_t)TC * EXT);  // [2S-1][HD+2]
   const int chunk = blockIdx.x, h = blockIdx.y, wb = blockIdx.z;
   const int t0 = chunk * TC;
   const int nt = min(TC, L - t0);
@@ -259,54 +259,58 @@ attn_prep_kernel(const __half* __restrict__ qkv, int ldq, const float* __restric
       }
     }
   }
-  // ---- phase 2: rel_h(q, j) = q . Rh[ty - j + S-1] ; rel_w(q, j) = q . Rw[tx - j + S-1]   (4x4 register tiles)
+  // ---- phase 2: rel_h(q, j) = q . Rh[ty - j + S-1] ; rel_w(q, j) = q . Rw[tx - j + S-1]
+  // work item = 2 horizontally adjacent tokens x JT offsets j.  Both tokens share the grid row, so for rel_h they need the
+  // SAME JT table rows, and for rel_w rows shifted by one (JT+1 distinct rows): ~10 shared-memory loads per 56 FMAs.
+  const int JT = (S % 8 == 0) ? 8 : 7;
+  const int njt = (S + JT - 1) / JT;
+  const int npair = TC / 2;
+  constexpr int RP = HD + 2;  // table row pitch (even: float2 loads)
   for (int pass = 0; pass < 2; ++pass) {
     const float* R = pass == 0 ? relh : relw;
     __syncthreads();
-    for (int i = tid; i < (2 * S - 1) * HD; i += 256) sr[(i / HD) * (HD + 1) + (i % HD)] = R[i];
+    for (int i = tid; i < (2 * S - 1) * HD; i += 256) sr[(i / HD) * RP + (i % HD)] = R[i];
     __syncthreads();
-    const int ntile_t = (TC + 3) / 4, ntile_j = (S + 3) / 4;
-    for (int tile = tid; tile < ntile_t * ntile_j; tile += 256) {
-      const int tb = (tile / ntile_j) * 4, jb = (tile % ntile_j) * 4;
-      float acc[4][4];
+    for (int item = tid; item < npair * njt; item += 256) {
+      const int pr = item / njt, jb = (item % njt) * JT;
+      const int tl = 2 * pr;                       // local token index of the pair's first token
+      if (tl >= nt) continue;
+      const int tt = t0 + tl;
+      const int ty = tt / S, tx0 = tt % S;         // S is even -> tl+1 lies in the same grid row
+      float acc0[8], acc1[8];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int e = 0; e < 8; ++e) { acc0[e] = 0.f; acc1[e] = 0.f; }
+      // table row of slot e:  pass 0: ty - (jb+e) + S-1 ;  pass 1: (tx0+1) - (jb+e) + S-1   (slot e serves token1 @ j=jb+e
+      // and token0 @ j=jb+e-1)
+      int rrow[9];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-      int ridx[4][4];
-      const __half* qrow[4];
+      for (int e = 0; e < 9; ++e) {
+        int idx = (pass == 0 ? ty : tx0 + 1) - (jb + e) + S - 1;
+        rrow[e] = min(max(idx, 0), 2 * S - 2) * RP;
+      }
+      const __half* q0 = sq + (size_t)tl * QP;
+      const __half* q1 = q0 + QP;
+      for (int d = 0; d < HD; d += 2) {
+        const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(q0 + d));
+        const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(q1 + d));
+        float2 rr[9];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int tl = min(tb + a, TC - 1);
-        qrow[a] = sq + (size_t)tl * QP;
-        const int tt = t0 + tl;
-        const int pos = pass == 0 ? (tt / S) : (tt % S);
+        for (int e = 0; e < 9; ++e) rr[e] = *reinterpret_cast<const float2*>(sr + rrow[e] + d);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int j = min(jb + b, S - 1);
-          ridx[a][b] = min(max(pos - j + S - 1, 0), 2 * S - 2) * (HD + 1);
+        for (int e = 0; e < 8; ++e) {
+          const float2 r0 = (pass == 0) ? rr[e] : rr[e + 1];  // token0 at j = jb+e
+          acc0[e] = fmaf(a0.x, r0.x, acc0[e]);
+          acc0[e] = fmaf(a0.y, r0.y, acc0[e]);
+          acc1[e] = fmaf(a1.x, rr[e].x, acc1[e]);
+          acc1[e] = fmaf(a1.y, rr[e].y, acc1[e]);
         }
       }
-      for (int d = 0; d < HD; d += 2) {
-        float2 qv[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) qv[a] = __half22float2(*reinterpret_cast<const __half2*>(qrow[a] + d));
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            acc[a][b] = fmaf(qv[a].x, sr[ridx[a][b] + d], acc[a][b]);
-            acc[a][b] = fmaf(qv[a].y, sr[ridx[a][b] + d + 1], acc[a][b]);
-          }
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int t = tb + a;
-        if (t >= TC) continue;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int j = jb + b;
-          if (j < S) qext[(size_t)t * EXT + pass * S + j] = __float2half_rn(acc[a][b]);
+      for (int e = 0; e < 8; ++e) {
+        const int j = jb + e;
+        if (e < JT && j < S) {
+          qext[(size_t)tl * EXT + pass * S + j] = __float2half_rn(acc0[e]);
+          qext[(size_t)(tl + 1) * EXT + pass * S + j] = __float2half_rn(acc1[e]);
         }
       }
     }
@@ -327,7 +331,7 @@ int attn_prep(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* 
   SAMPT_CHECK(D % 8 == 0 && ldq % 8 == 0, "attn_prep: D and ldq must be multiples of 8");
   dim3 grid(cdiv(L, TC), nheads, nwb);
   const int EXT = DK - HD;
-  size_t smem = (size_t)TC * (HD + 8) * 2 * 2 + (size_t)TC * EXT * 2 + (size_t)(2 * S - 1) * (HD + 1) * sizeof(float);
+  size_t smem = (size_t)TC * (HD + 8) * 2 * 2 + (size_t)TC * EXT * 2 + (size_t)(2 * S - 1) * (HD + 2) * sizeof(float);
   if (HD == 80) {
     static bool set80 = false;
     if (!set80) { SAMPT_CUDA(cudaFuncSetAttribute(attn_prep_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set80 = true; }
