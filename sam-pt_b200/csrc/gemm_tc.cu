@@ -85,9 +85,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(G_BM, G_BN, ep.is_bf16);
       uint32_t it = 0, tl = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        // narrow problems (N < 256, e.g. 64-channel convolutions) issue a narrower UMMA instead of multiplying zero padding
+        const int n_rem = N - (tile % n_tiles) * G_BN;
+        const int mma_n = n_rem >= G_BN ? G_BN : ((n_rem + 15) / 16) * 16;
+        const uint32_t idesc = make_idesc_f16(G_BM, mma_n, ep.is_bf16);
         const int acc = tl & 1;
         const uint32_t aph = (tl >> 1) & 1;
         mbar_wait(&tempty_bar[acc], aph ^ 1);

@@ -32,6 +32,9 @@ struct PipsWin {
 
 int conv_nhwc_f32(Ctx* c, cudaStream_t st, const float* in, const float* w, const float* bias, float* out, int Nimg,
                   int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, const int* skip = nullptr);
+int im2col_nhwc_split(Ctx* c, cudaStream_t st, const float* in, __half* A, int Nimg, int H, int W, int Cin, int R, int S, int stride,
+                      int pad, int Kp);
+int im2col_conv1_u8_split(Ctx* c, cudaStream_t st, const uint8_t* frames, __half* A, int Nimg, int H, int W, int Kp);
 int inorm_stats(Ctx* c, cudaStream_t st, const float* x, float* stats, double* part, int Nimg, int HW, int C);
 int inorm_apply(Ctx* c, cudaStream_t st, const float* x, const float* stats, const float* res, const float* res_stats,
                 float* y, int Nimg, int HW, int C, int relu_before_add, int relu_after);

@@ -200,6 +200,88 @@ int conv_nhwc_f32(Ctx* c, cudaStream_t st, const float* in, const float* w, cons
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core path of the encoder's convolutions: explicit im2col into the fp16 hi|lo operand layout of gemm_tc (3-pass
+// split precision ~ fp32), the GEMM then writes fp32 NHWC + bias.  Row m = output pixel, column k = (r*S + s)*Cin + ci,
+// K padded to a multiple of 64 with zeros; `lo` half at column offset Kp.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void im2col_nhwc_split_kernel(const float* __restrict__ in, __half* __restrict__ A, int Nimg, int H, int W, int Cin,
+                                         int Ho, int Wo, int R, int S, int stride, int pad, int Kp, long long total) {
+  // one thread = 8 consecutive k (16 B of hi + 16 B of lo)
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kg = (int)(i % (Kp / 8));
+  const long long m = i / (Kp / 8);
+  const int k0 = kg * 8;
+  const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), img = (int)(m / ((long long)Wo * Ho));
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  const int K = R * S * Cin;
+  if (k0 < K) {
+    const int tap = k0 / Cin, c0 = k0 % Cin;  // Cin % 8 == 0 -> the 8 k's share one tap
+    const int iy = oy * stride + tap / S - pad, ix = ox * stride + tap % S - pad;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const float* src = in + (((size_t)img * H + iy) * W + ix) * Cin + c0;
+      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+  }
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi[j] = __float2half_rn(v[j]);
+    lo[j] = __float2half_rn(v[j] - __half2float(hi[j]));
+  }
+  __half* row = A + (size_t)m * (2 * Kp);
+  *reinterpret_cast<uint4*>(row + k0) = *reinterpret_cast<uint4*>(hi);
+  *reinterpret_cast<uint4*>(row + Kp + k0) = *reinterpret_cast<uint4*>(lo);
+}
+int im2col_nhwc_split(Ctx* c, cudaStream_t st, const float* in, __half* A, int Nimg, int H, int W, int Cin, int R, int S, int stride,
+                      int pad, int Kp) {
+  SAMPT_CHECK(Cin % 8 == 0 && Kp % 64 == 0 && Kp >= R * S * Cin, "im2col_nhwc_split: Cin %% 8, Kp %% 64 required");
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const long long total = (long long)Nimg * Ho * Wo * (Kp / 8);
+  im2col_nhwc_split_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, A, Nimg, H, W, Cin, Ho, Wo, R, S, stride, pad, Kp, total);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  return 0;
+}
+// first layer: 7x7 stride 2 pad 3 on uint8 planar frames, normalisation 2*(x/255)-1 fused; k = (r*7 + s)*3 + ci, Kp = 192
+__global__ void im2col_conv1_u8_split_kernel(const uint8_t* __restrict__ frames, __half* __restrict__ A, int H, int W, int Ho,
+                                             int Wo, int Kp, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kg = (int)(i % (Kp / 8));
+  const long long m = i / (Kp / 8);
+  const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), img = (int)(m / ((long long)Wo * Ho));
+  const uint8_t* f = frames + (size_t)img * 3 * H * W;
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = kg * 8 + j;
+    float v = 0.f;
+    if (k < 147) {
+      const int tap = k / 3, ci = k % 3;
+      const int iy = oy * 2 + tap / 7 - 3, ix = ox * 2 + tap % 7 - 3;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = 2.0f * ((float)f[(size_t)ci * H * W + (size_t)iy * W + ix] / 255.0f) - 1.0f;
+    }
+    hi[j] = __float2half_rn(v);
+    lo[j] = __float2half_rn(v - __half2float(hi[j]));
+  }
+  __half* row = A + (size_t)m * (2 * Kp);
+  *reinterpret_cast<uint4*>(row + kg * 8) = *reinterpret_cast<uint4*>(hi);
+  *reinterpret_cast<uint4*>(row + Kp + kg * 8) = *reinterpret_cast<uint4*>(lo);
+}
+int im2col_conv1_u8_split(Ctx* c, cudaStream_t st, const uint8_t* frames, __half* A, int Nimg, int H, int W, int Kp) {
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const long long total = (long long)Nimg * Ho * Wo * (Kp / 8);
+  im2col_conv1_u8_split_kernel<<<cdiv(total, 256), 256, 0, st>>>(frames, A, H, W, Ho, Wo, Kp, total);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  return 0;
+}
+
 // InstanceNorm2d (no affine, eps 1e-5, biased variance; pips.py:207-209), channels-last.
 // pass 1: per (image, row-chunk) partial sum / sum of squares per channel.
 __global__ void inorm_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int HW, int C, int chunk) {

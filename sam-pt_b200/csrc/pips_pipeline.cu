@@ -5,6 +5,7 @@
 //   sampt_pips_track     : sliding-window chain with trajectory linking                        pips/tracker.py:42-153
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_api.cuh"
 #include "../../include/sampt_b200.h"
 
 namespace sampt {
@@ -21,7 +22,28 @@ static int alloc_act(Ctx* c, Act* a, int n, int h, int w, int ch, const char* wh
 
 struct FnetScratch { float* stats_a; float* stats_b; double* part; };
 
+static bool fnet_uses_tc(const Ctx* c) {
+  const TensorRef* f = c->find("pips.fnet.tc_flag");
+  return f != nullptr && f->dims[0] == 1 && c->find("pips.fnet.conv2.w16") != nullptr;
+}
+
+// scratch for the tensor-core convolution path (im2col operand); null -> strict fp32 CUDA-core convolutions
+static __half* g_im2col = nullptr;
+
 static int conv_by_name(Ctx* c, cudaStream_t st, const std::string& name, const Act& in, Act* out, int R, int stride, int pad) {
+  if (g_im2col != nullptr) {
+    // implicit-GEMM on tcgen05: A = im2col(in) as fp16 hi|lo, B = weights hi|lo, 3 split passes (~fp32), fp32 NHWC output
+    const __half* w16; const float* b;
+    SAMPT_TRY(get_f16(c, "pips." + name + ".w16", &w16));
+    SAMPT_TRY(get_f32(c, "pips." + name + ".bias", &b));
+    const int K = R * R * in.c, Kp = ((K + 63) / 64) * 64;
+    SAMPT_TRY(im2col_nhwc_split(c, st, in.p, g_im2col, in.n, in.h, in.w, in.c, R, R, stride, pad, Kp));
+    const int Ho = (in.h + 2 * pad - R) / stride + 1, Wo = (in.w + 2 * pad - R) / stride + 1;
+    GemmSeg seg{3, {0, Kp, 0}, {0, 0, Kp}};
+    GemmEpi ep{};
+    ep.out32 = out->p; ep.bias = b; ep.ldc = out->c;
+    return gemm_tc(c, st, g_im2col, 2 * Kp, w16, 2 * Kp, in.n * Ho * Wo, out->c, Kp, seg, ep);
+  }
   const float *w, *b;
   SAMPT_TRY(get_f32(c, "pips." + name + ".weight_rsck", &w));
   SAMPT_TRY(get_f32(c, "pips." + name + ".bias", &b));
@@ -69,14 +91,29 @@ static int fnet_chunk(Ctx* c, cudaStream_t st, const uint8_t* frames, int n, int
   int nchunks = cdiv((long long)H2 * W2, 512);
   SAMPT_TRY(ws_get(c, &s.part, (size_t)n * nchunks * 256 * 2, "inorm partials"));
 
-  const float *w1, *b1;
-  SAMPT_TRY(get_f32(c, "pips.fnet.conv1.weight_rsck", &w1));
-  SAMPT_TRY(get_f32(c, "pips.fnet.conv1.bias", &b1));
   Act x{bufA, n, H2, W2, 64};
-  dim3 g(cdiv((long long)H2 * W2, 64), n);
-  conv7x7s2_u8_kernel<<<g, 256, 0, st>>>(frames, w1, b1, x.p, H, W, H2, W2);
-  c->launches++;
-  SAMPT_LAUNCH_CHECK();
+  g_im2col = nullptr;
+  if (fnet_uses_tc(c)) {
+    // largest im2col operand: max(layer1: H2*W2 x 2*576, conv2: Ho*Wo x 2*3776) halves per frame
+    size_t a_elems = std::max((size_t)H2 * W2 * 2 * 576, (size_t)Ho * Wo * 2 * 3776) * n;
+    SAMPT_TRY(ws_get(c, &g_im2col, a_elems, "fnet im2col operand"));
+    const __half* w16; const float* b1;
+    SAMPT_TRY(get_f16(c, "pips.fnet.conv1.w16", &w16));
+    SAMPT_TRY(get_f32(c, "pips.fnet.conv1.bias", &b1));
+    SAMPT_TRY(im2col_conv1_u8_split(c, st, frames, g_im2col, n, H, W, 192));
+    GemmSeg seg{3, {0, 192, 0}, {0, 0, 192}};
+    GemmEpi ep{};
+    ep.out32 = x.p; ep.bias = b1; ep.ldc = 64;
+    SAMPT_TRY(gemm_tc(c, st, g_im2col, 384, w16, 384, n * H2 * W2, 64, 192, seg, ep));
+  } else {
+    const float *w1, *b1;
+    SAMPT_TRY(get_f32(c, "pips.fnet.conv1.weight_rsck", &w1));
+    SAMPT_TRY(get_f32(c, "pips.fnet.conv1.bias", &b1));
+    dim3 g(cdiv((long long)H2 * W2, 64), n);
+    conv7x7s2_u8_kernel<<<g, 256, 0, st>>>(frames, w1, b1, x.p, H, W, H2, W2);
+    c->launches++;
+    SAMPT_LAUNCH_CHECK();
+  }
   SAMPT_TRY(inorm_stats(c, st, x.p, s.stats_a, s.part, n, H2 * W2, 64));
   SAMPT_TRY(inorm_apply(c, st, x.p, s.stats_a, nullptr, nullptr, x.p, n, H2 * W2, 64, 1, 0));
 
@@ -125,6 +162,8 @@ extern "C" int sampt_pips_fnet(sampt_ctx* ctx, const uint8_t* frames_u8, int T, 
   // chunk frames so the fp32 half-res activations fit the workspace (6 buffers of n*H2*W2*64 floats + concat)
   const int H2 = (H + 6 - 7) / 2 + 1, W2 = (W + 6 - 7) / 2 + 1;
   size_t per_frame = ((size_t)H2 * W2 * 64 * 5 + (size_t)Ho * Wo * 416) * sizeof(float) + (1 << 20);
+  if (fnet_uses_tc(c))
+    per_frame += std::max((size_t)H2 * W2 * 2 * 576, (size_t)Ho * Wo * 2 * 3776) * sizeof(__half);
   int chunk = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, (c->ws_bytes - (8u << 20)) / per_frame));
   SAMPT_CHECK(c->ws_bytes > per_frame + (8u << 20), "workspace too small for one frame of fnet (%zu needed)", per_frame + (8u << 20));
   if (chunk > 16) chunk = 16;

@@ -3,6 +3,7 @@ SURVEY Appendix A.4) whose arithmetic runs in libsampt_b200 (csrc/pips_kernels.c
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_float, c_int
 from typing import Dict, Optional, Tuple
 
@@ -62,18 +63,32 @@ class Pips(nn.Module):
         self.corr_radius = 3
         build_param_tree(self, _pips_shapes(S), seed=486124)
         self._registered_on = None
+        # BasicEncoder convolutions as im2col + tcgen05 GEMM with 3-pass fp16 split (~fp32); "0" = strict fp32 CUDA-core path
+        self.fnet_on_tensor_cores = os.environ.get("SAMPT_PIPS_TC", "1") != "0"
 
     # ------------------------------------------------------------------ weights -> kernel-native layouts
     def native_context(self) -> native.Context:
         dev = self.norm.weight.device
         ctx = native.get_context(dev)
-        key = (id(ctx), tuple(p._version for p in self.parameters()), dev)
+        key = (id(ctx), tuple(p._version for p in self.parameters()), dev, self.fnet_on_tensor_cores)
         if self._registered_on != key:
             sd = self.state_dict()
+            # path selector read by sampt_pips_fnet (shape [1] = tensor-core convolutions, shape [2] = fp32 CUDA cores)
+            ctx.set_tensor("pips.fnet.tc_flag", torch.zeros(1 if self.fnet_on_tensor_cores else 2, dtype=torch.int32,
+                                                            device=self.norm.weight.device))
             for k, v in sd.items():
                 v = v.detach().float()
                 if k.startswith("fnet.") and k.endswith(".weight") and v.dim() == 4:
                     ctx.set_tensor(f"pips.{k}_rsck", v.permute(2, 3, 1, 0).contiguous())
+                    if self.fnet_on_tensor_cores:
+                        # tcgen05 path: [Cout, 2*Kp] fp16 hi|lo, k = (r*S + s)*Cin + ci, K zero-padded to a multiple of 64
+                        w = v.permute(0, 2, 3, 1).reshape(v.shape[0], -1)
+                        kp = -(-w.shape[1] // 64) * 64
+                        wp = torch.zeros((w.shape[0], kp), device=w.device)
+                        wp[:, : w.shape[1]] = w
+                        hi = wp.half()
+                        lo = (wp - hi.float()).half()
+                        ctx.set_tensor(f"pips.{k[:-len('.weight')]}.w16", torch.cat([hi, lo], dim=1).contiguous())
                 elif k == "delta_block.to_delta.0.weight":
                     w = torch.zeros((v.shape[0], 520), device=v.device)
                     w[:, : v.shape[1]] = v

@@ -50,7 +50,7 @@ def stream_ptr() -> c_void_p:
 class Context:
     """Owns one sampt_ctx on a device, its workspace slab and references to every registered tensor."""
 
-    def __init__(self, device: torch.device, workspace_bytes: int = 4 << 30):
+    def __init__(self, device: torch.device, workspace_bytes: int = 8 << 30):
         if not torch.cuda.is_available():
             raise RuntimeError("libsampt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device)

@@ -155,3 +155,16 @@ def test_batch_size_gt1_raises(sd, tmp_path):
     trk = _tracker(sd, tmp_path)
     with pytest.raises(NotImplementedError):
         trk(torch.zeros((2, 4, 3, 32, 32), dtype=torch.uint8).cuda(), torch.zeros((2, 1, 3)).cuda())
+
+
+def test_fnet_fp32_cuda_core_path_matches_oracle(sd):
+    """The strict-fp32 CUDA-core convolution path (SAMPT_PIPS_TC=0) stays available and parity-checked."""
+    from sam_pt.point_tracker.pips import Pips
+    m = Pips(S=8, stride=4)
+    m.fnet_on_tensor_cores = False
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    clip = synth.make_clip(2, 60, 106, seed=6)
+    ref = pips_ref.fnet(sd, 2 * (clip["frames"].float() / 255.0) - 1.0)
+    got = m.encode_frames(clip["frames"].cuda())[0].permute(0, 3, 1, 2).cpu()
+    assert (got - ref).abs().max() < 2e-5 * max(ref.abs().max().item(), 1.0)
