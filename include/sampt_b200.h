@@ -117,10 +117,13 @@ int sampt_sam_predict(sampt_ctx* ctx, const float* feat_tok, int G, const float*
                       const float* box, const float* mask_input, int multimask, int in_h, int in_w, int H, int W, float* logits,
                       float* iou, float* low_res, void* stream);
 /* SamPt.predict_mask (sam_pt.py:760-837) fused: [positive-only call +] full call + n_refine box/mask refinements with the
- * `mask area < 2` break evaluated on the device (no host synchronisation).  n_refine_done: device int32 [1]. */
+ * `mask area < 2` break evaluated on the device (no host synchronisation).  n_refine_done: device int32 [1].
+ * graph_slot selects an independent buffer set / CUDA-graph instance (decoder slab), so chains of different frames may be
+ * replayed concurrently on different streams. */
 int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const float* coords, const int* labels, int K,
                              const float* pos_coords, const int* pos_labels, int n_pos_first, int n_refine, int in_h, int in_w,
-                             int H, int W, float* logits, float* iou, float* low_res, int* n_refine_done, void* stream);
+                             int H, int W, float* logits, float* iou, float* low_res, int* n_refine_done, int graph_slot,
+                             void* stream);
 
 /* HQ-SAM (segment_anything_hq.modeling.mask_decoder_hq.MaskDecoderHQ, un-vendored m43/sam-hq @ 75c73fa; config
  * configs/model/sam/samhq_vit_huge.yaml:19-27).  sampt_sam_hq_features computes the per-frame

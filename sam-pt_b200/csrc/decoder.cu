@@ -1095,7 +1095,7 @@ extern "C" int sampt_ctx_set_decoder_workspace(sampt_ctx* ctx, void* dev_ptr, si
 extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const float* coords, const int* labels, int K,
                                         const float* pos_coords, const int* pos_labels, int n_pos_first, int n_refine, int in_h,
                                         int in_w, int H, int W, float* logits, float* iou, float* low_res, int* n_refine_done,
-                                        void* stream) {
+                                        int graph_slot, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DecW w;
@@ -1115,7 +1115,9 @@ extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, i
     return enqueue_refine_chain(c, st, w, b, s, p);
   }
   const bool hq = w.hq && c->hq_feat != nullptr;
-  std::vector<int> key{G, K, s.npos, n_refine, in_h, in_w, H, W, w.n_out_tok, hq ? 1 : 0};
+  // graph_slot: independent buffer sets / graph instances so that several frames' chains can replay CONCURRENTLY on
+  // different streams (each chain is a long sequence of tiny kernels: latency-, not throughput-bound)
+  std::vector<int> key{G, K, s.npos, n_refine, in_h, in_w, H, W, w.n_out_tok, hq ? 1 : 0, graph_slot};
   RefineGraph* g = nullptr;
   auto it = c->graph_cache.find(key);
   if (it == c->graph_cache.end()) {

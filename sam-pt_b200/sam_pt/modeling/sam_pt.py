@@ -53,6 +53,10 @@ class SamPt(nn.Module):
         # (fp32 CUDA-core pipes, latency bound): the two halves of the path do not depend on each other until decode
         self.overlap_streams = os.environ.get("SAMPT_OVERLAP", "1") != "0"
         self._enc_stream = None
+        # the per-frame decode chains (13 predict_torch calls = ~500 tiny kernels each) are latency bound and independent:
+        # replay them round-robin on several streams, each with its own CUDA-graph instance / buffers
+        self.decode_streams = int(os.environ.get("SAMPT_DECODE_STREAMS", "4"))
+        self._dec_streams = None
         self.outputs_on_cpu = False     # reference returns CPU tensors; keeping them on the device avoids a 82 MB copy
         self.frame_annotations = []
 
@@ -204,30 +208,54 @@ class SamPt(nn.Module):
         n_ref = int(self.iterative_refinement_iterations) if self.iterative_refinement_iterations else 0
         B = max(1, int(self.encoder_batch))
         want_interm = pred._uses_interm()
+        main = torch.cuda.current_stream()
+        nslot = max(1, int(self.decode_streams))
+        if nslot > 1 and (self._dec_streams is None or len(self._dec_streams) != nslot):
+            self._dec_streams = [torch.cuda.Stream(device=dev) for _ in range(nslot)]
+        used = set()
+        thr = float(self.sam_iou_threshold)
         for ci, f0 in enumerate(range(0, n_sub, B)):
             chunk = images[f0:f0 + B]
+            ev = None
             if pre is not None:  # encoder output produced on the encoder stream (see _start_encoder)
                 enc, ev = pre[ci]
-                torch.cuda.current_stream().wait_event(ev)
             else:
                 enc = pred.encode_frames(chunk, want_interm=want_interm)
+                if nslot > 1:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
             feats, interm = enc if want_interm else (enc, None)
             for j in range(chunk.shape[0]):
                 i = f0 + j
                 f = frame_ids[i]
-                pred.set_frames_features((height, width), (feats[j:j + 1], interm[j:j + 1]) if want_interm else feats[j:j + 1])
-                for m in range(n_masks):
-                    coords, labels = prepare_points(f, m)
-                    if len(coords) == 0:
-                        continue  # all points invisible -> mask stays -inf, score -inf (sam_pt.py:766-767,855)
-                    c1024 = torch.as_tensor(pred.transform.apply_coords(coords, pred.original_size), dtype=torch.float, device=dev)
-                    lab = torch.as_tensor(labels, dtype=torch.int, device=dev)
-                    iou, _, _ = pred.predict_refine(c1024, lab, 1 if self.negative_points_per_mask > 0 else 0, n_ref, logits[m, i])
-                    # "Mask is empty if SAM's IoU score is too low" (sam_pt.py:833-835), without a host round trip
-                    logits[m, i] = torch.where(iou[0] < self.sam_iou_threshold, torch.full_like(logits[m, i], -float("inf")),
-                                               logits[m, i])
-                    scores_pf[i, m] = iou[0]
-                    counted[i, m] = True
+                slot = i % nslot
+                stream = self._dec_streams[slot] if nslot > 1 else main
+                if nslot > 1 and slot not in used:
+                    stream.wait_stream(main)  # logits / scores buffers were created on the main stream
+                    used.add(slot)
+                with torch.cuda.stream(stream):
+                    if ev is not None:
+                        stream.wait_event(ev)
+                    pred.set_frames_features((height, width), (feats[j:j + 1], interm[j:j + 1]) if want_interm else feats[j:j + 1])
+                    for m in range(n_masks):
+                        coords, labels = prepare_points(f, m)
+                        if len(coords) == 0:
+                            continue  # all points invisible -> mask stays -inf, score -inf (sam_pt.py:766-767,855)
+                        c1024 = torch.as_tensor(pred.transform.apply_coords(coords, pred.original_size), dtype=torch.float, device=dev)
+                        lab = torch.as_tensor(labels, dtype=torch.int, device=dev)
+                        iou, _, _ = pred.predict_refine(c1024, lab, 1 if self.negative_points_per_mask > 0 else 0, n_ref, logits[m, i],
+                                                        slot=slot)
+                        # "Mask is empty if SAM's IoU score is too low" (sam_pt.py:833-835), without a host round trip
+                        logits[m, i] = torch.where(iou[0] < thr, torch.full_like(logits[m, i], -float("inf")), logits[m, i])
+                        scores_pf[i, m] = iou[0]
+                        counted[i, m] = True
+            if nslot > 1:
+                for t in (enc if isinstance(enc, tuple) else (enc,)):
+                    for sl in used:
+                        t.record_stream(self._dec_streams[sl])
+        if nslot > 1:
+            for sl in used:
+                main.wait_stream(self._dec_streams[sl])
         return logits, scores_pf, counted
 
     # ------------------------------------------------------------------------------------------------ multi-GPU

@@ -69,7 +69,7 @@ class Context:
         self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         check(lib().sampt_ctx_set_workspace(self._h, ptr(self._ws), c_size_t(nbytes)), "set_workspace")
 
-    def set_decoder_workspace(self, nbytes: int = 768 << 20) -> None:
+    def set_decoder_workspace(self, nbytes: int = 1536 << 20) -> None:
         """(Re)install the stable-address slab of the SAM decode chain; drops cached CUDA graphs."""
         self._dec_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         check(lib().sampt_ctx_set_decoder_workspace(self._h, ptr(self._dec_ws), c_size_t(nbytes)), "set_decoder_workspace")

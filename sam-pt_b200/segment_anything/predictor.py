@@ -166,7 +166,7 @@ class SamPredictor:
     # ------------------------------------------------------------------ fused SAM-PT refinement chain
     @torch.no_grad()
     def predict_refine(self, coords_1024: torch.Tensor, labels: torch.Tensor, n_positive_first: int, n_refine: int,
-                       logits_out: torch.Tensor):
+                       logits_out: torch.Tensor, slot: int = 0):
         """SamPt.predict_mask (sam_pt/modeling/sam_pt.py:781-828) as ONE native call: 1 (or 2) initial predict_torch calls
         + `n_refine` box/mask refinement iterations with the break test on the device.  coords (K,2), labels (K,) int32 on
         the GPU; writes logits into `logits_out` (H,W) and returns (iou (1,), low_res (256,256), n_done (1,) int32)."""
@@ -189,5 +189,5 @@ class SamPredictor:
             ctx.handle, native.ptr(tok), c_int(g), native.ptr(coords_1024.contiguous()), native.ptr(labels.contiguous()), c_int(K),
             native.ptr(pos_c), native.ptr(pos_l), c_int(n_positive_first), c_int(n_refine), c_int(self.input_size[0]),
             c_int(self.input_size[1]), c_int(H), c_int(W), native.ptr(logits_out), native.ptr(iou), native.ptr(low),
-            native.ptr(ndone), native.stream_ptr()), "sam_predict_refine")
+            native.ptr(ndone), c_int(slot), native.stream_ptr()), "sam_predict_refine")
         return iou, low, ndone

@@ -52,9 +52,9 @@ class SamPredictor(_Base):
             native.check(native.lib().sampt_sam_set_hq_features(self.model.native_context().handle, None), "set_hq")
 
     @torch.no_grad()
-    def predict_refine(self, coords_1024, labels, n_positive_first, n_refine, logits_out):
+    def predict_refine(self, coords_1024, labels, n_positive_first, n_refine, logits_out, slot=0):
         self._select_hq(True)
         try:
-            return super().predict_refine(coords_1024, labels, n_positive_first, n_refine, logits_out)
+            return super().predict_refine(coords_1024, labels, n_positive_first, n_refine, logits_out, slot)
         finally:
             native.check(native.lib().sampt_sam_set_hq_features(self.model.native_context().handle, None), "set_hq")
