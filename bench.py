@@ -199,7 +199,7 @@ def run_ours(args):
             "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
             "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split x3 (~fp32)"}[args.precision]
+            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split (3 passes MLP, 2 passes qkv/proj)", 4: "f16 hi+lo split x3 (~fp32)"}[args.precision]
                      + " ViT; f32 PIPS + decoder",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS (S=8, stride 4), 1 mask x {P} points, "
@@ -275,7 +275,7 @@ def run_ours_frame_sharded(args, model, dev, rank, world, local):
             "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
             "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split x3 (~fp32)"}[args.precision]
+            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split (3 passes MLP, 2 passes qkv/proj)", 4: "f16 hi+lo split x3 (~fp32)"}[args.precision]
                      + " ViT; f32 PIPS + decoder",
             "data": "synthetic",
             "config": {"workload": f"{world} x {args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS, 1 mask x {P} points, 12 refinements; "
@@ -402,7 +402,7 @@ def gemm_roofline(model, dev, args):
     enc = model.sam_predictor.model.image_encoder
     D, B = enc.embed_dim, args.encoder_batch
     M, N, K = B * 4096, 4 * D, D
-    p = args.precision
+    p = min(args.precision, 3)
     asp, bsp = (2 if p >= 3 else 1), (2 if p >= 2 else 1)
     A = torch.randn((M, K * asp), device=dev).half()
     Wt = torch.randn((N, K * bsp), device=dev).half()

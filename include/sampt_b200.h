@@ -101,7 +101,8 @@ int sampt_pil_resize_u8(sampt_ctx* ctx, const uint8_t* in, int B, int H, int W, 
                         uint8_t* out, void* stream);
 /* Sam.preprocess + ImageEncoderViT.forward for a batch of resized uint8 frames (B,3,Hr,Wr) -> features (B,C,g,g) fp32
  * [+ interm (B,g,g,D): output of the first global-attention block, HQ-SAM].  global_idx / pixel_mean / pixel_std are
- * HOST arrays.  precision: see sampt_gemm_f16.  Replaces SamPredictor.set_image's encoder call (sam_pt.py:849). */
+ * HOST arrays.  precision: 1/2 as in sampt_gemm_f16 for every GEMM; 3 = 3 split passes for the MLP / patch-embed / neck GEMMs
+ * and 2 (weights split) for qkv / proj, whose activations are fp16-limited by the attention path; 4 = 3 passes everywhere.  Replaces SamPredictor.set_image's encoder call (sam_pt.py:849). */
 int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B, int Hr, int Wr, int depth, int embed_dim, int num_heads,
                      int window_size, const int* global_idx_host, int n_global, int img_size, int patch_size, int out_chans,
                      int precision, const float* pixel_mean_host, const float* pixel_std_host, float* features, float* interm,

@@ -41,6 +41,12 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int H
   const int D = d.D, G = d.G, GG = G * G, HD = D / d.nheads, ws = d.window;
   const int nW = (G + ws - 1) / ws, Lw = ws * ws;
   const int Mtok = B * GG, Mwin = B * nW * nW * Lw;
+  // precision 3 ("mixed", default): MLP / patch-embed / neck GEMMs run all three split passes; the qkv and proj GEMMs run
+  // two (weights split).  Their activations are bounded by the fp16 attention path anyway: qkv's OUTPUT is rounded to
+  // fp16 for the attention operands and proj's INPUT is the fp16-P x fp16-V attention output, so the A_lo.W_hi pass would add
+  // precision that the neighbouring fp16 rounding discards.  precision 4 = all GEMMs three passes.
+  const int p_attn = precision == 3 ? 2 : (precision >= 4 ? 3 : precision);
+  if (precision >= 4) precision = 3;
   const int asp = precision >= 3 ? 2 : 1;  // A operands (activations) carried as hi|lo
   const int bsp = precision >= 2 ? 2 : 1;  // B operands (weights) carried as hi|lo
   const int Kpe = 3 * d.P * d.P;
@@ -110,21 +116,21 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int H
     const int Lkp = is_global ? GG : Lkpw;
     const int NT = is_global ? 128 : (((Lw + 15) / 16) * 16 <= 256 ? ((Lw + 15) / 16) * 16 : 128);
     // LN1 (+ window partition with zero padding)
-    SAMPT_TRY(ln_rows(c, st, x, D, is_global ? nullptr : wmap, n1w, n1b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mrows, D, 1));
+    SAMPT_TRY(ln_rows(c, st, x, D, is_global ? nullptr : wmap, n1w, n1b, 1e-6f, A, D * asp, (asp == 2 && p_attn == 3) ? D : 0, Mrows, D, 1));
     // qkv = Linear(D, 3D)
     {
       GemmEpi ep{};
       ep.out16 = qkv; ep.bias = qkvb; ep.ldc = 3 * D;
-      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wqkv, D * bsp, Mrows, 3 * D, D, make_seg(precision, D), ep));
+      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wqkv, D * bsp, Mrows, 3 * D, D, make_seg(p_attn, D), ep));
     }
     // attention
     SAMPT_TRY(attn_prep(c, st, qkv, 3 * D, rph, rpw, Qx, Kx, Vt, nwb, d.nheads, S, Lkp, DK, D, HD, 1.0f / sqrtf((float)HD)));
-    SAMPT_TRY(attn_tc(c, st, Qx, Kx, Vt, nwb * d.nheads, L, L, Lkp, DK, HD, NT, d.nheads, att, D * asp, asp == 2 ? D : 0));
+    SAMPT_TRY(attn_tc(c, st, Qx, Kx, Vt, nwb * d.nheads, L, L, Lkp, DK, HD, NT, d.nheads, att, D * asp, (asp == 2 && p_attn == 3) ? D : 0));
     // x = x + proj(attn)   (window un-partition via the row map; padding rows are dropped)
     {
       GemmEpi ep{};
       ep.out32 = x; ep.resid = x; ep.bias = projb; ep.ldc = D; ep.rowmap = is_global ? nullptr : wmap;
-      SAMPT_TRY(gemm_tc(c, st, att, D * asp, wproj, D * bsp, Mrows, D, D, make_seg(precision, D), ep));
+      SAMPT_TRY(gemm_tc(c, st, att, D * asp, wproj, D * bsp, Mrows, D, D, make_seg(p_attn, D), ep));
     }
     // x = x + lin2(gelu(lin1(LN2(x))))
     SAMPT_TRY(ln_rows(c, st, x, D, nullptr, n2w, n2b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mtok, D, 1));
@@ -181,7 +187,7 @@ extern "C" int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B
                                 int patch_size, int out_chans, int precision, const float* pixel_mean_host,
                                 const float* pixel_std_host, float* features, float* interm, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
-  SAMPT_CHECK(precision >= 1 && precision <= 3, "sampt_vit_encode: precision must be 1..3");
+  SAMPT_CHECK(precision >= 1 && precision <= 4, "sampt_vit_encode: precision must be 1..4");
   SAMPT_CHECK(img_size % patch_size == 0, "img_size must be a multiple of patch_size");
   SAMPT_CHECK(Hr <= img_size && Wr <= img_size, "resized image (%dx%d) exceeds img_size %d", Hr, Wr, img_size);
   SAMPT_CHECK(embed_dim % 128 == 0 && embed_dim % num_heads == 0, "embed_dim must be a multiple of 128 and of num_heads");

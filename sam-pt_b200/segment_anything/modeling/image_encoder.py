@@ -16,6 +16,8 @@ from sampt_b200.param_tree import build_param_tree
 
 # GEMM accuracy dial (DESIGN.md "precision"): 1 = fp16 operands single pass; 2 = WEIGHTS carried as fp16 hi|lo (exact
 # weights, fp16-rounded activations; 2 tensor-core passes); 3 = activations carried as hi|lo too (~fp32, 3 passes).
+# 3 is "mixed": qkv / proj GEMMs use 2 passes (their activations are fp16-limited by the attention path), the MLP GEMMs 3;
+# 4 = three passes everywhere.
 # Measured on C1 against the oracle: weight rounding is the coherent error that moves masks; activation rounding averages
 # out (IoU 0.9986 / see gpurun precision_dial / 0.99996 for 1 / 2 / 3).
 DEFAULT_PRECISION = int(os.environ.get("SAMPT_VIT_PRECISION", "3"))
