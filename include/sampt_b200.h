@@ -134,6 +134,31 @@ int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const
 int sampt_sam_hq_features(sampt_ctx* ctx, const float* feat_tok, const float* interm_tok, int G, float* out, void* stream);
 int sampt_sam_set_hq_features(sampt_ctx* ctx, const float* hq_features);
 
+/* ---- CoTracker point tracker (configs/model/point_tracker/cotracker.yaml; sam_pt/point_tracker/cotracker/tracker.py) ---
+ * The model itself is the un-vendored facebookresearch/co-tracker @ 4f297a9 (requirements.txt:31), checkpoint
+ * cotracker_stride_4_wind_8: PARITY UNPINNED (no golden vectors in the reference; see oracle/cotracker_ref.py). */
+/* F.interpolate(rgbs.float(), interp_shape, mode="bilinear") of CoTrackerPointTracker.forward (tracker.py:79-81):
+ * uint8 planar (planes,H,W) -> float32 planar (planes,Ho,Wo), align_corners=False. */
+int sampt_resize_bilinear_u8_f32(sampt_ctx* ctx, const uint8_t* in, int planes, int H, int W, int Ho, int Wo, float* out,
+                                 void* stream);
+/* CoTracker's BasicEncoder (weights "cot.fnet.*") over float32 frames (T,3,H,W) holding 0..255 -> (T,H/4,W/4,128)
+ * channels-last; replaces `self.fnet(2*(rgbs/255)-1)` of upstream CoTracker.forward, once per frame instead of per window. */
+int sampt_cotracker_fnet(sampt_ctx* ctx, const float* frames_f32, int T, int H, int W, float* fmaps, void* stream);
+/* feat_init of the points that enter a window (upstream CoTracker.forward: bilinear_sample2d of the point's first-frame
+ * feature map at its query coordinate): frame_dev (N) int32 frame index, xy_dev (N,2) feature-map px -> out (N,S,128),
+ * the sample repeated over the S slots. */
+int sampt_cotracker_sample_features(sampt_ctx* ctx, const float* fmaps, int H4, int W4, const int* frame_dev, const float* xy_dev,
+                                    int N, int S, float* out, void* stream);
+/* One sliding window of upstream CoTracker.forward_iteration (called through tracker.py:104,159 `self.model(rgbs, queries,
+ * iters=6)`): `iters` x { correlation gather, flow/position/time embeddings, UpdateFormer (time/space attention blocks),
+ * feature + coordinate update }, then the visibility head.  S = 8 slots.  fidx_dev: device int32[10] = {0, 0, frame index
+ * feeding slot 0..7}; coords (N,8,2) feature-map px IN/OUT; ffeats (N,8,128) IN/OUT; track_mask, vis_init (N,8) fp32;
+ * time_emb (8,456) fp32 sincos table; vis_out (N,8) raw visibility logits. */
+int sampt_cotracker_window(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3, int H4, int W4,
+                           const int* fidx_dev, float* coords, float* ffeats, const float* track_mask, const float* vis_init,
+                           const float* time_emb, int N, int iters, int time_depth, int space_depth, float* vis_out,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

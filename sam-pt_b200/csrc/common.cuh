@@ -134,6 +134,11 @@ __device__ __forceinline__ float warp_max(float v) {
 // exact (erf) GELU, as torch.nn.GELU() default
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// tanh-approximated GELU, torch.nn.GELU(approximate="tanh")
+__device__ __forceinline__ float gelu_tanh(float x) {
+  return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+}
+
 // block-wide sum for blockDim.x <= 1024; `red` must hold 32 floats
 __device__ __forceinline__ float block_sum(float v, float* red) {
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -4,7 +4,7 @@
 
 namespace sampt {
 
-// ---- fp32 GEMM (sgemm.cu):  Y = act(X W^T + bias) (+ residual);  act: 0 none, 1 GELU(erf), 2 ReLU
+// ---- fp32 GEMM (sgemm.cu):  Y = act(X W^T + bias) (+ residual);  act: 0 none, 1 GELU(erf), 2 ReLU, 3 GELU(tanh)
 int sgemm_nt(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias,
              const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int act);
 
@@ -34,7 +34,9 @@ int conv_nhwc_f32(Ctx* c, cudaStream_t st, const float* in, const float* w, cons
                   int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, const int* skip = nullptr);
 int im2col_nhwc_split(Ctx* c, cudaStream_t st, const float* in, __half* A, int Nimg, int H, int W, int Cin, int R, int S, int stride,
                       int pad, int Kp);
-int im2col_conv1_u8_split(Ctx* c, cudaStream_t st, const uint8_t* frames, __half* A, int Nimg, int H, int W, int Kp);
+int im2col_conv1_split(Ctx* c, cudaStream_t st, const void* frames, int is_f32, __half* A, int Nimg, int H, int W, int Kp);
+int conv7x7s2(Ctx* c, cudaStream_t st, const void* frames, int is_f32, const float* w, const float* bias, float* out, int Nimg,
+              int H, int W);
 int inorm_stats(Ctx* c, cudaStream_t st, const float* x, float* stats, double* part, int Nimg, int HW, int C);
 int inorm_apply(Ctx* c, cudaStream_t st, const float* x, const float* stats, const float* res, const float* res_stats,
                 float* y, int Nimg, int HW, int C, int relu_before_add, int relu_after);
@@ -51,9 +53,6 @@ int mixer_mean(Ctx* c, cudaStream_t st, const float* xln, float* xm, int N, int 
 int pips_update(Ctx* c, cudaStream_t st, const PipsWin& w, const float* delta, const float* gn_w, const float* gn_b,
                 const float* up_w, const float* up_b);
 int pips_link(Ctx* c, cudaStream_t st, const PipsWin& w, const float* vis_w, const float* vis_b, float thr0, int T);
-
-__global__ void conv7x7s2_u8_kernel(const uint8_t* frames, const float* w, const float* bias, float* out, int H, int W,
-                                    int Ho, int Wo);
 
 }  // namespace sampt
 

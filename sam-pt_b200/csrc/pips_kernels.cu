@@ -14,8 +14,9 @@ namespace sampt {
 
 // conv1: 7x7 stride 2 pad 3, 3 -> 64, input = uint8 planar frames normalised on the fly 2*(x/255)-1 (pips.py:446).
 // weights [kh][kw][ci][co] (co contiguous).  One thread = one output pixel x 16 output channels.
+template <typename TIn>
 __global__ void __launch_bounds__(256)
-conv7x7s2_u8_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ w, const float* __restrict__ bias,
+conv7x7s2_kernel(const TIn* __restrict__ frames, const float* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ out, int H, int W, int Ho, int Wo) {
   __shared__ float ws[7 * 7 * 3 * 64];
   for (int i = threadIdx.x; i < 7 * 7 * 3 * 64; i += blockDim.x) ws[i] = w[i];
@@ -25,7 +26,7 @@ conv7x7s2_u8_kernel(const uint8_t* __restrict__ frames, const float* __restrict_
   const long long pix = (long long)blockIdx.x * 64 + (threadIdx.x >> 2);
   if (pix >= (long long)Ho * Wo) return;
   const int oy = (int)(pix / Wo), ox = (int)(pix % Wo);
-  const uint8_t* f = frames + (size_t)img * 3 * H * W;
+  const TIn* f = frames + (size_t)img * 3 * H * W;
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = bias[cg * 16 + j];
@@ -47,6 +48,17 @@ conv7x7s2_u8_kernel(const uint8_t* __restrict__ frames, const float* __restrict_
   float* o = out + ((size_t)img * Ho * Wo + pix) * 64 + cg * 16;
 #pragma unroll
   for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+}
+
+int conv7x7s2(Ctx* c, cudaStream_t st, const void* frames, int is_f32, const float* w, const float* bias, float* out, int Nimg,
+              int H, int W) {
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  dim3 g(cdiv((long long)Ho * Wo, 64), Nimg);
+  if (is_f32) conv7x7s2_kernel<float><<<g, 256, 0, st>>>((const float*)frames, w, bias, out, H, W, Ho, Wo);
+  else conv7x7s2_kernel<uint8_t><<<g, 256, 0, st>>>((const uint8_t*)frames, w, bias, out, H, W, Ho, Wo);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  return 0;
 }
 
 // Generic implicit-GEMM convolution, channels-last, fp32:  out[n,oy,ox,co] = bias[co] + sum_{r,s,ci} in[n,iy,ix,ci] * w[r,s,ci,co]
@@ -248,14 +260,15 @@ int im2col_nhwc_split(Ctx* c, cudaStream_t st, const float* in, __half* A, int N
   return 0;
 }
 // first layer: 7x7 stride 2 pad 3 on uint8 planar frames, normalisation 2*(x/255)-1 fused; k = (r*7 + s)*3 + ci, Kp = 192
-__global__ void im2col_conv1_u8_split_kernel(const uint8_t* __restrict__ frames, __half* __restrict__ A, int H, int W, int Ho,
+template <typename TIn>
+__global__ void im2col_conv1_split_kernel(const TIn* __restrict__ frames, __half* __restrict__ A, int H, int W, int Ho,
                                              int Wo, int Kp, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int kg = (int)(i % (Kp / 8));
   const long long m = i / (Kp / 8);
   const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), img = (int)(m / ((long long)Wo * Ho));
-  const uint8_t* f = frames + (size_t)img * 3 * H * W;
+  const TIn* f = frames + (size_t)img * 3 * H * W;
   __half hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -273,10 +286,14 @@ __global__ void im2col_conv1_u8_split_kernel(const uint8_t* __restrict__ frames,
   *reinterpret_cast<uint4*>(row + kg * 8) = *reinterpret_cast<uint4*>(hi);
   *reinterpret_cast<uint4*>(row + Kp + kg * 8) = *reinterpret_cast<uint4*>(lo);
 }
-int im2col_conv1_u8_split(Ctx* c, cudaStream_t st, const uint8_t* frames, __half* A, int Nimg, int H, int W, int Kp) {
+// frames: uint8 (is_f32 == 0) or float32 holding 0..255 values (is_f32 == 1, the CoTracker wrapper's resized clip)
+int im2col_conv1_split(Ctx* c, cudaStream_t st, const void* frames, int is_f32, __half* A, int Nimg, int H, int W, int Kp) {
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   const long long total = (long long)Nimg * Ho * Wo * (Kp / 8);
-  im2col_conv1_u8_split_kernel<<<cdiv(total, 256), 256, 0, st>>>(frames, A, H, W, Ho, Wo, Kp, total);
+  if (is_f32)
+    im2col_conv1_split_kernel<float><<<cdiv(total, 256), 256, 0, st>>>((const float*)frames, A, H, W, Ho, Wo, Kp, total);
+  else
+    im2col_conv1_split_kernel<uint8_t><<<cdiv(total, 256), 256, 0, st>>>((const uint8_t*)frames, A, H, W, Ho, Wo, Kp, total);
   c->launches++;
   SAMPT_LAUNCH_CHECK();
   return 0;

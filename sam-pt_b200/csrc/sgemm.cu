@@ -117,6 +117,7 @@ sgemm_nt_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ 
       if (bias) v += bias[gn];
       if (act == 1) v = gelu_erf(v);
       else if (act == 2) v = fmaxf(v, 0.f);
+      else if (act == 3) v = gelu_tanh(v);
       if (residual) v += residual[(size_t)gm * ldr + gn];
       Y[(size_t)gm * ldy + gn] = v;
     }
@@ -171,6 +172,7 @@ sgemm_smallm_kernel(const float* __restrict__ X, int ldx, const float* __restric
       if (bias) v += bias[n];
       if (act == 1) v = gelu_erf(v);
       else if (act == 2) v = fmaxf(v, 0.f);
+      else if (act == 3) v = gelu_tanh(v);
       if (residual) v += residual[(size_t)m * ldr + n];
       Y[(size_t)m * ldy + n] = v;
     }
@@ -270,6 +272,7 @@ sgemm_pipe_kernel(const float* __restrict__ X, int ldx, const float* __restrict_
       if (bias) v += bias[gn];
       if (act == 1) v = gelu_erf(v);
       else if (act == 2) v = fmaxf(v, 0.f);
+      else if (act == 3) v = gelu_tanh(v);
       if (residual) v += residual[(size_t)gm * ldr + gn];
       Y[(size_t)gm * ldy + gn] = v;
     }

@@ -155,3 +155,13 @@ def write_pips_checkpoint_dir(sd: Dict[str, torch.Tensor], path: str, step: int 
     os.makedirs(path, exist_ok=True)
     torch.save({"model_state_dict": sd}, os.path.join(path, "model-%09d.pth" % step))
     return path
+
+
+def condition_cotracker(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """x0.1 on the UpdateFormer's flow head keeps random-weight CoTracker updates small (tracks stay inside the frame) and a
+    visibility bias spreads sigmoid(vis) around the reference's 0.7 threshold (configs/model/point_tracker/cotracker.yaml:7)."""
+    sd = dict(sd)
+    sd["updateformer.flow_head.weight"] = sd["updateformer.flow_head.weight"] * 0.1
+    sd["updateformer.flow_head.bias"] = sd["updateformer.flow_head.bias"] * 0.1
+    sd["vis_predictor.0.bias"] = sd["vis_predictor.0.bias"] - 0.55
+    return sd

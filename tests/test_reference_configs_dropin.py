@@ -66,3 +66,28 @@ def test_default_hq_config_instantiates(tmp_path):
     import segment_anything_hq.predictor as hp
     assert type(model.sam_predictor) is hp.SamPredictor
     assert "mask_decoder.hf_token.weight" in model.sam_predictor.model.state_dict()
+
+
+def test_default_cotracker_config_instantiates(tmp_path):
+    """configs/model/sam_pt.yaml with NO tracker override: the reference's default point tracker is CoTracker
+    (sam_pt.yaml:3, configs/model/point_tracker/cotracker.yaml); a checkpoint written with upstream's key names loads."""
+    from oracle import cotracker_ref
+    from sampt_b200 import hydra_lite, synth
+    sd = synth.condition_cotracker(synth.make_state_dict(cotracker_ref.cotracker_state_dict_shapes(), 3))
+    ck = tmp_path / "models" / "cotracker_ckpts"
+    ck.mkdir(parents=True)
+    torch.save({"model": sd}, str(ck / "cotracker_stride_4_wind_8.pth"))
+    cfg = hydra_lite.compose_model(REF_CFG, {"sam_predictor.sam_model.checkpoint": None,
+                                             "sam_predictor.sam_model.image_encoder.depth": 2,
+                                             "sam_predictor.sam_model.image_encoder.global_attn_indexes": [1]}, cwd=str(tmp_path))
+    pt = cfg["point_tracker"]
+    assert pt["_target_"] == "sam_pt.point_tracker.cotracker.CoTrackerPointTracker"
+    assert pt["interp_shape"] == [384, 512] and pt["visibility_threshold"] == 0.7
+    assert pt["support_grid_size"] == 2 and pt["support_grid_every_n_frames"] == 12
+    model = hydra_lite.instantiate(cfg)
+    from sam_pt.point_tracker.cotracker import CoTrackerPointTracker
+    assert type(model.point_tracker) is CoTrackerPointTracker
+    got = model.point_tracker.model.state_dict()
+    assert set(got) == set(sd)
+    k = "updateformer.space_blocks.5.attn.qkv.weight"
+    assert torch.equal(got[k].cpu(), sd[k])
