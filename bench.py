@@ -35,7 +35,9 @@ CONFIGS = {
     "C2": (50, 480, 854, "vit_h", 8),
     "C2b": (50, 480, 854, "vit_b", 8),
     "C2p": (4, 480, 854, "vit_h", 8),   # profiling-sized slice of C2 (ncu launch lists)
+    "C3": (50, 480, 854, "vit_h", 64),  # BASELINE configs[2]: CoTracker (window 8), 64 query points
 }
+TRACKER = {"C3": "cotracker"}           # every other config tracks with PIPS
 SAM_SEED, PIPS_SEED = 7202, 7201
 
 
@@ -121,7 +123,14 @@ def run_ours(args):
     sam_sd, pips_sd = make_weights(vit)
     tmp = tempfile.mkdtemp(prefix="sampt_bench_")
     ckpt = synth.write_pips_checkpoint_dir(pips_sd, os.path.join(tmp, "pips"))
-    model = factory.build_sam_pt(vit, sam_sd, ckpt, positive_points_per_mask=P, sam_iou_threshold=-1e9, device=dev)
+    tracker = TRACKER.get(args.config, "pips")
+    cot_sd = None
+    if tracker == "cotracker":
+        from sam_pt.point_tracker.cotracker.cotracker import cotracker_shapes
+        cot_sd = synth.condition_cotracker(synth.make_state_dict(cotracker_shapes(), PIPS_SEED + 1))
+        args.no_cpu_baseline = True  # the CPU arm below times the PIPS path; C3 reports GPU numbers only
+    model = factory.build_sam_pt(vit, sam_sd, ckpt, positive_points_per_mask=P, sam_iou_threshold=-1e9, device=dev,
+                                 cotracker_state_dict=cot_sd)
     model.sam_predictor.model.image_encoder.precision = args.precision
     model.encoder_batch = args.encoder_batch
     if world > 1 and args.mgpu_mode == "frame_shard":
@@ -202,7 +211,7 @@ def run_ours(args):
             "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split (3 passes MLP, 2 passes qkv/proj)", 4: "f16 hi+lo split x3 (~fp32)"}[args.precision]
                      + " ViT; f32 PIPS + decoder",
             "data": "synthetic",
-            "config": {"workload": f"{args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS (S=8, stride 4), 1 mask x {P} points, "
+            "config": {"workload": f"{args.config}: {T} frames {H}x{W}, SAM {vit} + {'CoTracker (S=8, stride 4, interp 384x512)' if tracker == 'cotracker' else 'PIPS (S=8, stride 4)'}, 1 mask x {P} points, "
                                    f"12 refinement iterations, random-init conditioned weights",
                        "clips_per_step": world, "parallelism": f"clip-per-GPU x{world}" if world > 1 else "single GPU",
                        "l2": "flushed between timed iterations (256 MiB write)", "vit_precision_passes": args.precision,

@@ -54,7 +54,8 @@ def build_sam(vit: str = "vit_b", sam_state_dict: Optional[Dict[str, torch.Tenso
 
 
 def build_sam_pt(vit: str, sam_state_dict, pips_ckpt_dir: str, positive_points_per_mask: int, negative_points_per_mask: int = 0,
-                 iterative_refinement_iterations: int = 12, sam_iou_threshold: float = 0.7, device="cuda", hq: bool = False):
+                 iterative_refinement_iterations: int = 12, sam_iou_threshold: float = 0.7, device="cuda", hq: bool = False,
+                 cotracker_state_dict=None):
     """configs/model/sam_pt.yaml with `model/point_tracker=pips`, `model/sam@...=sam_vit_*` and the demo-style overrides
     positive_points_per_mask=P negative_points_per_mask=0 (demo/demo.py:107-110)."""
     from sam_pt.modeling.sam_pt import SamPt
@@ -65,7 +66,14 @@ def build_sam_pt(vit: str, sam_state_dict, pips_ckpt_dir: str, positive_points_p
         from segment_anything.predictor import SamPredictor
 
     sam = build_sam(vit, sam_state_dict, hq=hq)
-    tracker = PipsPointTracker(checkpoint_path=pips_ckpt_dir, stride=4, s=8, initial_next_frame_visibility_threshold=0.9)
+    if cotracker_state_dict is not None:
+        # configs/model/point_tracker/cotracker.yaml (the reference's default tracker group)
+        from sam_pt.point_tracker.cotracker import CoTrackerPointTracker
+        tracker = CoTrackerPointTracker(checkpoint_path=None, interp_shape=[384, 512], visibility_threshold=0.7, support_grid_size=2,
+                                        support_grid_every_n_frames=12, add_debug_visualisations=False)
+        tracker.model.load_state_dict(cotracker_state_dict)
+    else:
+        tracker = PipsPointTracker(checkpoint_path=pips_ckpt_dir, stride=4, s=8, initial_next_frame_visibility_threshold=0.9)
     model = SamPt(point_tracker=tracker, sam_predictor=SamPredictor(sam_model=sam), sam_iou_threshold=sam_iou_threshold,
                   positive_point_selection_method="kmedoids", negative_point_selection_method="mixed",
                   positive_points_per_mask=positive_points_per_mask, negative_points_per_mask=negative_points_per_mask,

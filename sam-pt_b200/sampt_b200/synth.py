@@ -158,10 +158,17 @@ def write_pips_checkpoint_dir(sd: Dict[str, torch.Tensor], path: str, step: int 
 
 
 def condition_cotracker(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """x0.1 on the UpdateFormer's flow head keeps random-weight CoTracker updates small (tracks stay inside the frame) and a
-    visibility bias spreads sigmoid(vis) around the reference's 0.7 threshold (configs/model/point_tracker/cotracker.yaml:7)."""
+    """Random-weight CoTracker is chaotic: the flow embedding carries frequencies up to ~970 rad per feature pixel, so with an
+    untrained O(1) coordinate head any 1e-6 perturbation saturates at ~0.6 px after 18 iterations (measured on the oracle
+    itself).  Scaling the two coordinate rows of the UpdateFormer's flow head by 0.003 (and the feature rows by 0.1) makes the
+    iteration contractive like the trained checkpoint (1e-5 relative feature noise -> 2e-5 px), which is what a parity test needs.
+    A visibility bias spreads sigmoid(vis) around the reference's 0.7 threshold (configs/model/point_tracker/cotracker.yaml:7)."""
     sd = dict(sd)
-    sd["updateformer.flow_head.weight"] = sd["updateformer.flow_head.weight"] * 0.1
-    sd["updateformer.flow_head.bias"] = sd["updateformer.flow_head.bias"] * 0.1
-    sd["vis_predictor.0.bias"] = sd["vis_predictor.0.bias"] - 0.55
+    w, b = sd["updateformer.flow_head.weight"].clone(), sd["updateformer.flow_head.bias"].clone()
+    w[:2] *= 0.003
+    b[:2] *= 0.003
+    w[2:] *= 0.1
+    b[2:] *= 0.1
+    sd["updateformer.flow_head.weight"], sd["updateformer.flow_head.bias"] = w, b
+    sd["vis_predictor.0.bias"] = sd["vis_predictor.0.bias"] - 0.9
     return sd

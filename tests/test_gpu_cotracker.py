@@ -12,6 +12,8 @@ INTERP = (96, 128)
 
 
 def _weights():
+    # conditioned random weights: an UNconditioned random CoTracker is chaotic (see synth.condition_cotracker), which would turn
+    # any comparison into a coin flip; the conditioned one is contractive like the trained checkpoint
     from sam_pt.point_tracker.cotracker.cotracker import cotracker_shapes
     return synth.condition_cotracker(synth.make_state_dict(cotracker_shapes(), seed=31))
 
@@ -76,7 +78,7 @@ def test_model_windows_vs_oracle():
     d = (traj.cpu() - traj_ref[0]).abs().max().item()
     dv = (vis.cpu() - vis_ref[0]).abs().max().item()
     print(f"cotracker model: max |traj - oracle| = {d:.2e} px, max |vis - oracle| = {dv:.2e}")
-    assert d < 2e-2 and dv < 2e-3
+    assert d < 2e-3 and dv < 2e-3
     # frames before the first window that contains a point stay exactly zero in the one-directional pass (the wrapper's
     # `traj == 0` merge relies on it): the point born at t=9 enters with the window starting at frame 4
     assert (traj[:4, 4] == 0).all() and (traj[4:, 4] != 0).all()
@@ -98,12 +100,12 @@ def test_tracker_wrapper_vs_oracle(T):
     d = (traj.cpu() - traj_ref).abs().max().item()
     agree = (vis.cpu() == vis_ref).float().mean().item()
     print(f"cotracker wrapper T={T}: max |traj - oracle| = {d:.2e} px, visibility agreement {agree:.3f}, visible {vis_ref.float().mean():.2f}")
-    assert d < 3e-2
+    assert d < 3e-3
     assert agree >= 0.97
 
 
 def test_tensor_core_encoder_end_to_end():
-    """default configuration (encoder convolutions on tcgen05 with the 3-pass split): trajectories within 0.1 px of the oracle."""
+    """default configuration (encoder convolutions on tcgen05 with the 3-pass split): trajectories within 0.02 px of the oracle."""
     from oracle import cotracker_ref as R
     sd = _weights()
     T, H, W = 12, 96, 128
@@ -115,4 +117,4 @@ def test_tensor_core_encoder_end_to_end():
     traj, _ = trk(frames[None].cuda(), q.cuda())
     d = (traj.cpu() - traj_ref).abs().max().item()
     print(f"cotracker wrapper (TC encoder): max |traj - oracle| = {d:.2e} px")
-    assert d < 0.1
+    assert d < 0.02
