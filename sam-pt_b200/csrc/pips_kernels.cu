@@ -301,25 +301,43 @@ int im2col_conv1_split(Ctx* c, cudaStream_t st, const void* frames, int is_f32, 
 
 // InstanceNorm2d (no affine, eps 1e-5, biased variance; pips.py:207-209), channels-last.
 // pass 1: per (image, row-chunk) partial sum / sum of squares per channel.
-__global__ void inorm_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int HW, int C, int chunk) {
-  const int img = blockIdx.z, ch = blockIdx.y;  // ch = chunk index
-  const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cidx >= C) return;
+// 256 threads = (C/4 float4 channel lanes) x (256/(C/4) pixel rows): 16-byte coalesced loads, `rows` pixels in flight per lane
+// group, fp32 partial sums over <= chunk/rows pixels promoted to fp64 before the cross-row / cross-chunk reduction.
+__global__ void __launch_bounds__(256)
+inorm_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int HW, int C, int chunk) {
+  const int img = blockIdx.z, ch = blockIdx.y;
+  const int c4n = C >> 2, rows = 256 / c4n;
+  const int lane4 = threadIdx.x % c4n, row = threadIdx.x / c4n;
   const int p0 = ch * chunk, p1 = min(HW, p0 + chunk);
-  const float* base = x + (size_t)img * HW * C + cidx;
-  float s = 0.f, ss = 0.f;
-  double ds = 0.0, dss = 0.0;
-  int cnt = 0;
-  for (int p = p0; p < p1; ++p) {
-    float v = base[(size_t)p * C];
-    s += v;
-    ss = fmaf(v, v, ss);
-    if (++cnt == 64) { ds += s; dss += ss; s = 0.f; ss = 0.f; cnt = 0; }
+  __shared__ double red[256][8];
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (row < rows) {
+    const float* base = x + (size_t)img * HW * C + lane4 * 4;
+    int cnt = 0;
+#pragma unroll 4
+    for (int p = p0 + row; p < p1; p += rows) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)p * C);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      ss.x = fmaf(v.x, v.x, ss.x); ss.y = fmaf(v.y, v.y, ss.y); ss.z = fmaf(v.z, v.z, ss.z); ss.w = fmaf(v.w, v.w, ss.w);
+      if (++cnt == 64) {
+        acc[0] += s.x; acc[1] += ss.x; acc[2] += s.y; acc[3] += ss.y; acc[4] += s.z; acc[5] += ss.z; acc[6] += s.w; acc[7] += ss.w;
+        s = make_float4(0.f, 0.f, 0.f, 0.f); ss = make_float4(0.f, 0.f, 0.f, 0.f); cnt = 0;
+      }
+    }
+    acc[0] += s.x; acc[1] += ss.x; acc[2] += s.y; acc[3] += ss.y; acc[4] += s.z; acc[5] += ss.z; acc[6] += s.w; acc[7] += ss.w;
   }
-  ds += s; dss += ss;
-  size_t o = (((size_t)img * gridDim.y + ch) * C + cidx) * 2;
-  part[o] = ds;
-  part[o + 1] = dss;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (row == 0) {
+    for (int r = 1; r < rows; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += red[r * c4n + lane4][k];
+    double* o = part + (((size_t)img * gridDim.y + ch) * C + lane4 * 4) * 2;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = acc[k];  // [c][sum, sumsq] for the 4 channels of this lane
+  }
 }
 __global__ void inorm_final_kernel(const double* __restrict__ part, float* __restrict__ stats, int nchunks, int C, int HW,
                                    float eps) {
@@ -377,8 +395,9 @@ __global__ void inorm_apply_kernel(const float* __restrict__ x, const float* __r
 int inorm_stats(Ctx* c, cudaStream_t st, const float* x, float* stats, double* part, int Nimg, int HW, int C) {
   const int chunk = 512;
   int nchunks = cdiv(HW, chunk);
-  dim3 g1(cdiv(C, 64), nchunks, Nimg);
-  inorm_partial_kernel<<<g1, 64, 0, st>>>(x, part, HW, C, chunk);
+  SAMPT_CHECK(C % 4 == 0 && C <= 1024, "inorm_stats: unsupported channel count %d", C);
+  dim3 g1(1, nchunks, Nimg);
+  inorm_partial_kernel<<<g1, 256, 0, st>>>(x, part, HW, C, chunk);
   SAMPT_LAUNCH_CHECK();
   dim3 g2(cdiv(C, 64), Nimg);
   inorm_final_kernel<<<g2, 64, 0, st>>>(part, stats, nchunks, C, HW, 1e-5f);

@@ -55,7 +55,7 @@ class SamPt(nn.Module):
         self._enc_stream = None
         # the per-frame decode chains (13 predict_torch calls = ~500 tiny kernels each) are latency bound and independent:
         # replay them round-robin on several streams, each with its own CUDA-graph instance / buffers
-        self.decode_streams = int(os.environ.get("SAMPT_DECODE_STREAMS", "4"))
+        self.decode_streams = int(os.environ.get("SAMPT_DECODE_STREAMS", "8"))
         self._dec_streams = None
         self.outputs_on_cpu = False     # reference returns CPU tensors; keeping them on the device avoids a 82 MB copy
         self.frame_annotations = []
@@ -275,6 +275,9 @@ class SamPt(nn.Module):
         world, rank = dist.get_world_size(), dist.get_rank()
         dev = self.device
         trk = self.point_tracker.to(dev)
+        if not hasattr(trk, "track_on_features"):
+            raise NotImplementedError("frame-sharded tracking is built for the PIPS tracker (BASELINE configs[3]); CoTracker clips "
+                                      "run one clip per GPU through SamPt.forward")
         C = len(videos)
         T = len(videos[0]["image"])
         own = sharding.owned_frames(T, rank, world)
