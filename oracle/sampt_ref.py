@@ -26,14 +26,19 @@ from . import pips_ref, sam_ref
 OUTSIDE_FRAME = -2  # PointVisibilityType.OUTSIDE_FRAME, sam_pt/utils/util.py:267-282
 
 
-def track_points(pips_sd, images_u8, query_points, mask_batch_size: int = 5):
-    """_track_points + __track_points_inner (sam_pt.py:545-596, 684-692). images (T,3,H,W) u8; query (M,P,3)."""
+def track_points(pips_sd, images_u8, query_points, mask_batch_size: int = 5, tracker=None):
+    """_track_points + __track_points_inner (sam_pt.py:545-596, 684-692). images (T,3,H,W) u8; query (M,P,3).
+    `tracker(images (1,T,3,H,W) u8, queries (1,N,3)) -> (traj (1,T,N,2), vis (1,T,N) bool)` replaces the PIPS tracker (e.g. the
+    CoTracker restatement, configs/model/point_tracker/cotracker.yaml); `pips_sd` is then unused."""
     M, P, _ = query_points.shape
     trajs, viss = [], []
     for i in range(0, M, mask_batch_size):
         q = query_points[i:i + mask_batch_size]
         m = q.shape[0]
-        traj, vis = pips_ref.pips_tracker_forward(pips_sd, images_u8[None], q.reshape(1, m * P, 3))
+        if tracker is not None:
+            traj, vis = tracker(images_u8[None], q.reshape(1, m * P, 3))
+        else:
+            traj, vis = pips_ref.pips_tracker_forward(pips_sd, images_u8[None], q.reshape(1, m * P, 3))
         traj, vis = traj[0], vis[0].float()
         traj = traj.reshape(-1, m, P, 2)
         vis = vis.reshape(-1, m, P)
@@ -129,14 +134,14 @@ def apply_sam_to_trajectories(predictor: sam_ref.RefSamPredictor, images_u8, tra
 def sampt_forward(pips_sd, predictor: sam_ref.RefSamPredictor, video: Dict, *, positive_points_per_mask: int,
                   negative_points_per_mask: int = 0, iterative_refinement_iterations: int = 12,
                   sam_iou_threshold: float = 0.7, point_tracker_mask_batch_size: int = 5,
-                  features_cache: Optional[dict] = None, taps: Optional[dict] = None):
+                  features_cache: Optional[dict] = None, taps: Optional[dict] = None, tracker=None):
     """SamPt.forward with the query_points branch (sam_pt.py:122-236)."""
     images = torch.stack(video["image"], dim=0)
     assert images.dtype == torch.uint8
     if video.get("query_points") is None:
         raise ValueError("No query points or masks provided")
     qp = video["query_points"]
-    traj, vis = track_points(pips_sd, images, qp, point_tracker_mask_batch_size)
+    traj, vis = track_points(pips_sd, images, qp, point_tracker_mask_batch_size, tracker=tracker)
     _, logits, spf = apply_sam_to_trajectories(
         predictor, images, traj, vis, positive_points_per_mask=positive_points_per_mask,
         negative_points_per_mask=negative_points_per_mask,

@@ -55,7 +55,7 @@ def build_sam(vit: str = "vit_b", sam_state_dict: Optional[Dict[str, torch.Tenso
 
 def build_sam_pt(vit: str, sam_state_dict, pips_ckpt_dir: str, positive_points_per_mask: int, negative_points_per_mask: int = 0,
                  iterative_refinement_iterations: int = 12, sam_iou_threshold: float = 0.7, device="cuda", hq: bool = False,
-                 cotracker_state_dict=None):
+                 cotracker_state_dict=None, cotracker_interp_shape=(384, 512)):
     """configs/model/sam_pt.yaml with `model/point_tracker=pips`, `model/sam@...=sam_vit_*` and the demo-style overrides
     positive_points_per_mask=P negative_points_per_mask=0 (demo/demo.py:107-110)."""
     from sam_pt.modeling.sam_pt import SamPt
@@ -69,7 +69,7 @@ def build_sam_pt(vit: str, sam_state_dict, pips_ckpt_dir: str, positive_points_p
     if cotracker_state_dict is not None:
         # configs/model/point_tracker/cotracker.yaml (the reference's default tracker group)
         from sam_pt.point_tracker.cotracker import CoTrackerPointTracker
-        tracker = CoTrackerPointTracker(checkpoint_path=None, interp_shape=[384, 512], visibility_threshold=0.7, support_grid_size=2,
+        tracker = CoTrackerPointTracker(checkpoint_path=None, interp_shape=list(cotracker_interp_shape), visibility_threshold=0.7, support_grid_size=2,
                                         support_grid_every_n_frames=12, add_debug_visualisations=False)
         tracker.model.load_state_dict(cotracker_state_dict)
     else:

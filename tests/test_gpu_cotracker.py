@@ -118,3 +118,42 @@ def test_tensor_core_encoder_end_to_end():
     d = (traj.cpu() - traj_ref).abs().max().item()
     print(f"cotracker wrapper (TC encoder): max |traj - oracle| = {d:.2e} px")
     assert d < 0.02
+
+
+@pytest.mark.parametrize("hq", [False, True])
+def test_sampt_with_cotracker_end_to_end(tmp_path, hq):
+    """BASELINE configs[2] / configs[4] in miniature: SamPt.forward with the CoTracker tracker (+ HQ-SAM), 2 masks x 4 points (mask
+    batching, other objects' positives as negatives, out-of-frame relabel), against the oracle of the whole path."""
+    from oracle import cotracker_ref as R, sam_ref, sampt_ref
+    from sampt_b200 import factory
+    cfg = sam_ref.VIT_TEST
+    sam_sd = synth.condition_sam(synth.make_state_dict(sam_ref.sam_state_dict_shapes(cfg, hq=hq), 47))
+    cot_sd = _weights()
+    video = synth.make_video_dict(10, 96, 128, 4, seed=13)   # seed chosen so that no sigmoid(vis) lies within 3e-3 of the threshold
+    q0 = video["query_points"]
+    q1 = q0.clone()
+    q1[..., 1] = (q1[..., 1] + 37.0) % 120.0 + 4.0
+    q1[..., 2] = (q1[..., 2] + 23.0) % 88.0 + 4.0
+    q1[..., 0] = 3.0                                  # second object annotated on frame 3 -> exercises the backward pass
+    video["query_points"] = torch.cat([q0, q1], dim=0)
+
+    def oracle_tracker(images, queries):
+        return R.cotracker_point_tracker_forward(cot_sd, images, queries, interp_shape=INTERP)
+
+    ref = sampt_ref.sampt_forward(None, sam_ref.RefSamPredictor(sam_sd, cfg, hq=hq), video, positive_points_per_mask=4,
+                                  sam_iou_threshold=-1e9, tracker=oracle_tracker)
+    model = factory.build_sam_pt("vit_test", sam_sd, None, positive_points_per_mask=4, sam_iou_threshold=-1e9, hq=hq,
+                                 cotracker_state_dict=cot_sd, cotracker_interp_shape=INTERP)
+    out = model(video)
+    terr = (out["trajectories"].cpu() - ref["trajectories"]).abs().max().item()
+    assert torch.equal(out["visibilities"].cpu(), ref["visibilities"])
+    ious = [_iou(out["logits"][m][f].cpu(), ref["logits"][m][f]) for m in range(2) for f in range(10)]
+    print(f"SamPt + CoTracker (hq={hq}): max |dcoord| = {terr:.2e} px, min mask IoU = {min(ious):.5f}")
+    assert terr < 1e-3
+    assert min(ious) >= 0.999
+
+
+def _iou(a, b):
+    a, b = a > 0, b > 0
+    u = (a | b).sum().item()
+    return ((a & b).sum().item() / u) if u else 1.0
