@@ -364,6 +364,16 @@ def stage_breakdown(model, frames_dev, q_dev):
     return {k: round(v, 3) for k, v in out.items()}
 
 
+def _ncu_traffic(key):
+    """DRAM bytes per launch (read + write) of a roofline kernel from the committed `ncu --set full` capture
+    (profiles/r01_roofline_traffic.json, produced by tools/ncu_targets.py + profiles/extract_traffic.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    e = json.load(open(p)).get(key)
+    return None if e is None else e["dram_read_bytes"] + e["dram_write_bytes"]
+
+
 def corr_roofline(dev, n_points=292):
     """Secondary roofline entry: the fused PIPS correlation gather (pips_corr lookup) at a large point count
     (C5-like: 256 queries + 36 support points), where it is bandwidth- rather than latency-bound.  Algorithmic bytes =
@@ -400,7 +410,7 @@ def corr_roofline(dev, n_points=292):
     pk = _peaks()
     gbs = nbytes / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "pips_corr_only_kernel (fused correlation gather, N=%d points)" % n_points, "achieved": gbs,
-            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None, "ms": ms,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": _ncu_traffic("pips_corr"), "ms": ms,
             "peak_source": pk["src"], "algorithmic_bytes": nbytes, "l2": "flushed before every launch"}
 
 
@@ -439,7 +449,8 @@ def gemm_roofline(model, dev, args):
     pk = _peaks()
     return {"bound": "tensor", "kernel": "gemm_tc_kernel (ViT mlp.lin1 shape)", "achieved": flops_exec / (ms * 1e-3) / 1e12,
             "achieved_algorithmic": flops_alg / (ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": flops_exec / (ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["src"] + ", burst",
+            "frac": flops_exec / (ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": _ncu_traffic("gemm_tc_kernel"), "algorithmic_bytes": 2.0 * (M * K * asp + N * K * bsp + M * N),
+            "peak_source": pk["src"] + ", burst",
             "shape": [M, N, K], "passes": p, "ms": ms}
 
 
