@@ -47,6 +47,9 @@ int sampt_ctx_set_decoder_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes)
 /* register a caller-owned device tensor under a name (weights in kernel-native layout; replaces the
  * load_state_dict contract of sam_pt/modeling/sam.py:18-31 and sam_pt/point_tracker/utils/saverloader.py:30-73) */
 int sampt_set_tensor(sampt_ctx* ctx, const char* name, void* dev_ptr, int dtype, int ndim, const int64_t* dims);
+/* forget every registered tensor whose name starts with `prefix` (a model that re-registers its weights first drops the
+ * names of whatever model used the prefix before, e.g. an HQ-SAM decoder followed by a plain SAM decoder) */
+int sampt_unset_tensors(sampt_ctx* ctx, const char* prefix);
 /* number of kernels launched through this ctx since creation (bench.py reports the delta as gpu_launches) */
 long long sampt_launch_count(sampt_ctx* ctx);
 

@@ -57,6 +57,15 @@ extern "C" int sampt_set_tensor(sampt_ctx* ctx, const char* name, void* dev_ptr,
   c->tensors[std::string(name)] = t;
   return 0;
 }
+extern "C" int sampt_unset_tensors(sampt_ctx* ctx, const char* prefix) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  const std::string p(prefix);
+  for (auto it = c->tensors.begin(); it != c->tensors.end();) {
+    if (it->first.compare(0, p.size(), p) == 0) it = c->tensors.erase(it);
+    else ++it;
+  }
+  return 0;
+}
 extern "C" long long sampt_launch_count(sampt_ctx* ctx) { return reinterpret_cast<Ctx*>(ctx)->launches; }
 
 extern "C" int sampt_linear_f32(sampt_ctx* ctx, const float* X, int ldx, const float* W, int ldw, const float* bias,

@@ -91,7 +91,8 @@ class CoTracker(nn.Module):
         dev = self.norm.weight.device
         ctx = native.get_context(dev)
         key = (id(ctx), tuple(p._version for p in self.parameters()), dev, self.fnet_on_tensor_cores)
-        if self._registered_on != key:
+        if self._registered_on != key or not ctx.owns("cot", self):
+            torch.cuda.synchronize(dev)  # nothing may still be reading the tensors this replaces
             ctx.set_tensor("cot.fnet.tc_flag", torch.zeros(1 if self.fnet_on_tensor_cores else 2, dtype=torch.int32, device=dev))
             for k, v in self.state_dict().items():
                 v = v.detach().float()
@@ -110,6 +111,7 @@ class CoTracker(nn.Module):
             ctx.set_tensor("cot.time_emb", _time_embed_table(IN_DIM, self.S).to(dev))
             self._time_emb = ctx._tensors["cot.time_emb"]
             self._registered_on = key
+            ctx.claim("cot", self)
         return ctx
 
     # ------------------------------------------------------------------ per-frame work

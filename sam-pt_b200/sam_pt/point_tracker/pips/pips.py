@@ -71,7 +71,8 @@ class Pips(nn.Module):
         dev = self.norm.weight.device
         ctx = native.get_context(dev)
         key = (id(ctx), tuple(p._version for p in self.parameters()), dev, self.fnet_on_tensor_cores)
-        if self._registered_on != key:
+        if self._registered_on != key or not ctx.owns("pips", self):
+            torch.cuda.synchronize(dev)  # nothing may still be reading the tensors this replaces
             sd = self.state_dict()
             # path selector read by sampt_pips_fnet (shape [1] = tensor-core convolutions, shape [2] = fp32 CUDA cores)
             ctx.set_tensor("pips.fnet.tc_flag", torch.zeros(1 if self.fnet_on_tensor_cores else 2, dtype=torch.int32,
@@ -96,6 +97,7 @@ class Pips(nn.Module):
                 else:
                     ctx.set_tensor(f"pips.{k}", v.contiguous())
             self._registered_on = key
+            ctx.claim("pips", self)
         return ctx
 
     # ------------------------------------------------------------------ building blocks used by the tracker

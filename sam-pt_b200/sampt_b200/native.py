@@ -58,6 +58,7 @@ class Context:
         with torch.cuda.device(self.device):
             check(lib().sampt_ctx_create(c_int(self.device.index or 0), ctypes.byref(self._h)), "ctx_create")
         self._tensors: Dict[str, torch.Tensor] = {}
+        self._owners: Dict[str, object] = {}
         self._ws = None
         self.set_workspace(workspace_bytes)
 
@@ -92,6 +93,23 @@ class Context:
         dims = (c_int64 * max(t.dim(), 1))(*t.shape)
         check(lib().sampt_set_tensor(self._h, name.encode(), ptr(t), c_int(_DTYPES[t.dtype]), c_int(t.dim()), dims),
               f"set_tensor({name})")
+
+    def owns(self, namespace: str, owner) -> bool:
+        """True when `owner` was the last module to register weights under `namespace` on this context.  Weight names are
+        shared per device, so a second model of the same kind takes the namespace over and the first one must re-register
+        before it runs again (its cached registration key alone cannot see that)."""
+        ref = self._owners.get(namespace)
+        return ref is not None and ref() is owner
+
+    def claim(self, namespace: str, owner) -> None:
+        import weakref
+        self._owners[namespace] = weakref.ref(owner)
+
+    def unset_prefix(self, prefix: str) -> None:
+        """Drop every registered tensor whose name starts with `prefix` (C registry and the Python references)."""
+        check(lib().sampt_unset_tensors(self._h, prefix.encode()), f"unset_tensors({prefix})")
+        for k in [k for k in self._tensors if k.startswith(prefix)]:
+            del self._tensors[k]
 
     def launch_count(self) -> int:
         return int(lib().sampt_launch_count(self._h))

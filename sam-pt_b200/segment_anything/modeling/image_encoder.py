@@ -71,7 +71,8 @@ class ImageEncoderViT(nn.Module):
         dev = self.pos_embed.device
         ctx = native.get_context(dev)
         key = (id(ctx), self.precision, tuple(p._version for p in self.parameters()), dev)
-        if self._registered != key:
+        if self._registered != key or not ctx.owns("sam.image_encoder", self):
+            torch.cuda.synchronize(dev)  # nothing may still be reading the tensors this replaces
             split_b = self.precision >= 2
             sd = self.state_dict()
             D = self.embed_dim
@@ -91,6 +92,7 @@ class ImageEncoderViT(nn.Module):
             for n in ("neck.1.weight", "neck.1.bias", "neck.3.weight", "neck.3.bias"):
                 ctx.set_tensor(prefix + n, sd[n].float())
             self._registered = key
+            ctx.claim("sam.image_encoder", self)
         return ctx
 
     def workspace_bytes(self, B: int) -> int:

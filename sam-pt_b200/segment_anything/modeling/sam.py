@@ -34,16 +34,21 @@ class Sam(nn.Module):
         ctx = self.image_encoder.native_context()
         key = (id(ctx), tuple(p._version for p in self.prompt_encoder.parameters()),
                tuple(p._version for p in self.mask_decoder.parameters()), self.device)
-        if self._dec_registered != key:
+        if self._dec_registered != key or not ctx.owns("sam.decoder", self):
             self._register_decoder(ctx)
             if self.use_cuda_graphs:
                 ctx.set_decoder_workspace()  # also invalidates graphs captured with the previous weights
             self._dec_registered = key
+            ctx.claim("sam.decoder", self)
         return ctx
 
     @torch.no_grad()
     def _register_decoder(self, ctx: native.Context) -> None:
         pe, md = self.prompt_encoder, self.mask_decoder
+        # another Sam (e.g. an HQ-SAM whose decoder has extra hf_* tensors) may have used these names on this device before
+        torch.cuda.synchronize(ctx.device)
+        ctx.unset_prefix("sam.prompt_encoder.")
+        ctx.unset_prefix("sam.mask_decoder.")
         for k, v in pe.state_dict().items():
             ctx.set_tensor("sam.prompt_encoder." + k, v.float().reshape(-1) if v.dim() == 2 and v.shape[0] == 1 else v.float())
         sd = md.state_dict()
