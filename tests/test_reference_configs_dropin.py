@@ -49,7 +49,7 @@ def test_vit_huge_override_composes():
 
 def test_default_hq_config_instantiates(tmp_path):
     """configs/model/sam_pt.yaml's own defaults select HQ-SAM ViT-H + `segment_anything_hq.predictor.SamPredictor`
-    (sam_pt.yaml:3-8); only the tracker group is switched to PIPS (CoTracker is not built yet)."""
+    (sam_pt.yaml:3-8); only the tracker group is switched to PIPS here; the no-override default is covered below."""
     from oracle import pips_ref
     from sampt_b200 import hydra_lite, synth
     pips_sd = synth.condition_pips(synth.make_state_dict(pips_ref.pips_state_dict_shapes(), 1))
