@@ -11,10 +11,8 @@ CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_DIR = os.path.join(PKG_ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsampt_b200.so")
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false" if False else "-Xcompiler", "-fvisibility=default",
-]
+# sm_100a only; no --use_fast_math: sinf/cosf/expf/erff must stay the accurate versions (flow embeddings reach ~1e5 rad)
+NVCC_COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:
@@ -53,8 +51,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         if (not force) and os.path.exists(obj) and os.path.getmtime(obj) > max(
                 os.path.getmtime(src), *[os.path.getmtime(os.path.join(CSRC, h)) for h in os.listdir(CSRC) if h.endswith(".cuh")]):
             continue
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-               "-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_COMPILE_FLAGS + ["-c", src, "-o", obj]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -64,7 +61,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out:
             print(out, file=sys.stderr)
-    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs + ["-lcuda" if False else "-lcudart"]
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
