@@ -27,4 +27,9 @@ int gemm_tc(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int 
 int attn_tc(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp,
             int DK, int HD, int NT, int nheads, __half* out, int ld_out, int split_off);
 
+// experimental pipelined variant for multi-tile attention (attn_tc_v2.cu); off unless SAMPT_ATTN_V2=1
+bool attn_tc_v2_applicable(int Lk, int DK, int HD);
+int attn_tc_v2(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp, int DK,
+               int HD, int nheads, __half* out, int ld_out, int split_off);
+
 }  // namespace sampt
