@@ -527,7 +527,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
             "value": v, "unit": "frames/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * T / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS, 1 mask x {P} points (bounded sample: "
+            "config": {"workload": (f"{os.environ['WORLD_SIZE']} x " if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "") +
+                                   f"{args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS, 1 mask x {P} points (bounded sample: "
                                    f"{base['sample']})"},
             "cpu_baseline": base, "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
