@@ -50,3 +50,35 @@ def test_allgather_frames_world2():
             assert p.exitcode == 0
         ok, ms = ret.get(timeout=10)
         assert ok == 1.0 and ms == 11.0
+
+
+def test_allgather_frames_world4_ragged():
+    """the 4- and 8-GPU scaling runs: 50 frames over 4 ranks (13,13,12,12 owned frames -> padded all-gather)."""
+    world, T = 4, 50
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, T, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    ok, ms = ret.get(timeout=10)
+    assert ok == 1.0 and ms == 10.0 + world - 1
+
+
+def test_owned_frames_partition_every_world_size():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "sam-pt_b200"))
+    from sampt_b200 import sharding
+    for world in (1, 2, 4, 8):
+        for T in (2, 50, 100):
+            owned = [sharding.owned_frames(T, r, world) for r in range(world)]
+            assert sorted(f for o in owned for f in o) == list(range(T))
+            n = sharding.padded_count(T, world)
+            assert all(len(o) <= n for o in owned) and max(len(o) for o in owned) == n
+            # the gather's reorder index is a permutation onto the un-padded rows
+            idx = [(f % world) * n + f // world for f in range(T)]
+            assert len(set(idx)) == T and all(i < world * n for i in idx)
