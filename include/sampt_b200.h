@@ -129,6 +129,10 @@ int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const
                              int H, int W, float* logits, float* iou, float* low_res, int* n_refine_done, int graph_slot,
                              void* stream);
 
+/* Forget the image-independent ViT rows saved by the experimental SAMPT_VIT_SKIP_PAD=1 path (csrc/vit_pipeline.cu); to be
+ * called whenever the image-encoder weights are re-registered.  A no-op when that path is off. */
+int sampt_vit_cache_clear(sampt_ctx* ctx);
+
 /* HQ-SAM (segment_anything_hq.modeling.mask_decoder_hq.MaskDecoderHQ, un-vendored m43/sam-hq @ 75c73fa; config
  * configs/model/sam/samhq_vit_huge.yaml:19-27).  sampt_sam_hq_features computes the per-frame
  * `embedding_encoder(image_embeddings) + compress_vit_feat(interm_embeddings[0])` map ([16*G*G][32], channels-last);

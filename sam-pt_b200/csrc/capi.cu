@@ -38,6 +38,7 @@ extern "C" int sampt_ctx_destroy(sampt_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return 0;
   if (c->pinned) cudaFreeHost(c->pinned);
+  for (auto& kv : c->owned) cudaFree(kv.second.first);
   delete c;
   return 0;
 }

@@ -74,6 +74,9 @@ struct Ctx {
   cudaStream_t cap_stream = nullptr;
   std::map<std::vector<int>, void*> graph_cache;
   const float* hq_feat = nullptr;  // HQ-SAM features of the current frame (decoder.cu), caller-owned
+  // library-owned device buffers that outlive a call (e.g. the ViT's image-independent padding tokens, vit_pipeline.cu);
+  // freed by sampt_vit_cache_clear / sampt_ctx_destroy
+  std::map<std::string, std::pair<void*, size_t>> owned;
 
   const TensorRef* find(const std::string& name) const {
     auto it = tensors.find(name);

@@ -2,6 +2,8 @@
 // Upstream: segment_anything/modeling/image_encoder.py (un-vendored); reference call site
 // sam_pt/modeling/sam_pt.py:849 (SamPredictor.set_image).  Frames are batched (B) so every GEMM has M = B*4096 (or
 // B*4900 window-partitioned rows) and fills 148 SMs.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_api.cuh"
@@ -18,6 +20,63 @@ __global__ void window_map_kernel(int* __restrict__ map, int B, int G, int ws, i
   int w = (int)(wb % (nW * nW)), b = (int)(wb / (nW * nW));
   int y = (w / nW) * ws + t / ws, x = (w % nW) * ws + t % ws;
   map[r] = (y < G && x < G) ? (b * G * G + y * G + x) : -1;
+}
+
+// ---- EXPERIMENTAL (SAMPT_VIT_SKIP_PAD=1, off by default, not yet validated on hardware) -------------------------
+// A non-square frame is zero-padded to 1024 x 1024 AFTER normalisation (upstream Sam.preprocess), so every token whose 14x14
+// window lies entirely in the padding is image-independent until the first GLOBAL attention block mixes all tokens: its
+// value after blocks 0..fg-1 is a constant of the model (weights + pos_embed).  For 480x854 input (576x1024 resized) that
+// is 10 of the 25 windows and 1408 of the 4096 tokens in 7 of ViT-H's 32 blocks.  The first encode of a (shape, weights)
+// pair runs in full and saves those rows; later encodes run blocks 0..fg-1 on the live windows / tokens only (compacted
+// index lists through the existing gather / row-map plumbing) and restore the saved rows before block fg.  Results are
+// bit-identical: a GEMM row, a LayerNorm row and a window's attention do not depend on the other rows of the batch.
+// live window w = (wy, wx) with wy < lwy, wx < lwx, row-major over the live sub-grid
+__global__ void live_window_map_kernel(int* __restrict__ map, int B, int G, int ws, int lwy, int lwx, long long total) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= total) return;
+  const int L = ws * ws;
+  int t = (int)(r % L);
+  long long wb = r / L;
+  int w = (int)(wb % (lwy * lwx)), b = (int)(wb / (lwy * lwx));
+  int y = (w / lwx) * ws + t / ws, x = (w % lwx) * ws + t % ws;
+  map[r] = (y < G && x < G) ? (b * G * G + y * G + x) : -1;
+}
+// live tokens: y < rows_live && x < cols_live, row-major
+__global__ void live_token_map_kernel(int* __restrict__ map, int B, int G, int rows_live, int cols_live, long long total) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= total) return;
+  const int per = rows_live * cols_live;
+  int i = (int)(r % per), b = (int)(r / per);
+  map[r] = b * G * G + (i / cols_live) * G + (i % cols_live);
+}
+// constant tokens of ONE frame (everything that is not live), any fixed order
+__global__ void const_token_map_kernel(int* __restrict__ map, int G, int rows_live, int cols_live) {
+  int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= G * G) return;
+  const int y = tok / G, x = tok % G;
+  if (y < rows_live && x < cols_live) return;
+  const int per_live_row = G - cols_live;
+  const int idx = y < rows_live ? y * per_live_row + (x - cols_live) : rows_live * per_live_row + (y - rows_live) * G + x;
+  map[idx] = tok;
+}
+// dst[i, :] = src[map[i], :]  (save)  /  dst[b*GG + map[i], :] = src[i, :] for every frame b  (restore)
+__global__ void rows_gather_kernel(const float* __restrict__ src, const int* __restrict__ map, float* __restrict__ dst, int n, int D4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * D4) return;
+  const int r = (int)(i / D4), c = (int)(i % D4);
+  reinterpret_cast<float4*>(dst)[(size_t)r * D4 + c] = reinterpret_cast<const float4*>(src)[(size_t)map[r] * D4 + c];
+}
+__global__ void rows_scatter_bcast_kernel(const float* __restrict__ src, const int* __restrict__ map, float* __restrict__ dst, int n, int D4,
+                                          int B, int GG) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * n * D4) return;
+  const int c = (int)(i % D4);
+  const int r = (int)((i / D4) % n), b = (int)(i / ((long long)D4 * n));
+  reinterpret_cast<float4*>(dst)[((size_t)b * GG + map[r]) * D4 + c] = reinterpret_cast<const float4*>(src)[(size_t)r * D4 + c];
+}
+static bool skip_pad_enabled() {
+  static const int on = [] { const char* e = std::getenv("SAMPT_VIT_SKIP_PAD"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+  return on != 0;
 }
 
 static GemmSeg make_seg(int precision, int K) {
@@ -81,6 +140,44 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int H
   c->launches++;
   SAMPT_LAUNCH_CHECK();
 
+  // ---- optional: skip the image-independent padding windows / tokens in the blocks before the first global block
+  int fg = d.depth;
+  for (int i = 0; i < n_global; ++i) fg = std::min(fg, global_idx[i]);
+  const int lwy = std::min(nW, (int)cdiv(cdiv(Hr, d.P), ws)), lwx = std::min(nW, (int)cdiv(cdiv(Wr, d.P), ws));
+  const int rows_live = std::min(G, lwy * ws), cols_live = std::min(G, lwx * ws);
+  const int nLW = lwy * lwx, nLT = rows_live * cols_live, n_const = GG - nLT;
+  const bool pad_candidate = skip_pad_enabled() && fg > 0 && fg < d.depth && n_const > 0;
+  int *wmap_c = nullptr, *tmap_c = nullptr, *cmap = nullptr;
+  float* x_const = nullptr;   // [n_const, D] saved rows (library-owned, survives the call)
+  bool compact = false;       // this call runs blocks < fg on the live rows only
+  bool save_const = false;    // this call runs in full and saves the constant rows before block fg
+  if (pad_candidate) {
+    char key[160];
+    snprintf(key, sizeof(key), "vitconst:%dx%d:g%d:w%d:d%d:D%d:fg%d:p%d", Hr, Wr, G, ws, d.depth, D, fg, precision * 10 + p_attn);
+    auto it = c->owned.find(key);
+    if (it == c->owned.end()) {
+      void* buf = nullptr;
+      SAMPT_CUDA(cudaMalloc(&buf, (size_t)n_const * D * sizeof(float)));
+      c->owned[key] = {buf, 0};   // second = 1 once the rows have been saved
+      it = c->owned.find(key);
+    }
+    x_const = reinterpret_cast<float*>(it->second.first);
+    compact = it->second.second == 1;
+    save_const = !compact;
+    SAMPT_TRY(ws_get(c, &cmap, (size_t)n_const, "vit const-token map"));
+    const_token_map_kernel<<<cdiv(GG, 256), 256, 0, st>>>(cmap, G, rows_live, cols_live);
+    c->launches++;
+    if (compact) {
+      SAMPT_TRY(ws_get(c, &wmap_c, (size_t)B * nLW * Lw, "vit live window map"));
+      SAMPT_TRY(ws_get(c, &tmap_c, (size_t)B * nLT, "vit live token map"));
+      live_window_map_kernel<<<cdiv((long long)B * nLW * Lw, 256), 256, 0, st>>>(wmap_c, B, G, ws, lwy, lwx, (long long)B * nLW * Lw);
+      live_token_map_kernel<<<cdiv((long long)B * nLT, 256), 256, 0, st>>>(tmap_c, B, G, rows_live, cols_live, (long long)B * nLT);
+      c->launches += 2;
+    }
+    SAMPT_LAUNCH_CHECK();
+    if (save_const) it->second.second = 2;  // "being saved by this call" (set to 1 below, after the copy is enqueued)
+  }
+
   // ---- patch embedding (Conv2d k=16 s=16 as a GEMM) + pos_embed
   {
     SAMPT_TRY(preprocess_im2col(c, st, img, A, B, Hr, Wr, G, d.P, Kpe * asp, asp == 2 ? Kpe : 0, mean, stdv));
@@ -108,15 +205,31 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int H
     SAMPT_TRY(get_f16(c, bp + "attn.qkv.w16", &wqkv)); SAMPT_TRY(get_f16(c, bp + "attn.proj.w16", &wproj));
     SAMPT_TRY(get_f16(c, bp + "mlp.lin1.w16", &wl1)); SAMPT_TRY(get_f16(c, bp + "mlp.lin2.w16", &wl2));
 
-    const int Mrows = is_global ? Mtok : Mwin;
+    if (blk == fg && pad_candidate) {
+      const int D4 = D / 4;
+      if (save_const) {        // full run: remember the image-independent rows (taken from frame 0)
+        rows_gather_kernel<<<cdiv((long long)n_const * D4, 256), 256, 0, st>>>(x, cmap, x_const, n_const, D4);
+        c->launches++;
+        SAMPT_LAUNCH_CHECK();
+        for (auto& kv : c->owned) if (kv.second.first == x_const) kv.second.second = 1;
+      } else if (compact) {    // compacted run: put them back before the first global block reads every token
+        rows_scatter_bcast_kernel<<<cdiv((long long)B * n_const * D4, 256), 256, 0, st>>>(x_const, cmap, x, n_const, D4, B, GG);
+        c->launches++;
+        SAMPT_LAUNCH_CHECK();
+      }
+    }
+    const bool live_only = compact && blk < fg;          // windowed block restricted to the live windows / tokens
+    const int Mrows = is_global ? Mtok : (live_only ? B * nLW * Lw : Mwin);
+    const int Mmlp = live_only ? B * nLT : Mtok;
+    const int* blk_wmap = live_only ? wmap_c : wmap;
     const int S = is_global ? G : ws;
     const int L = S * S;
-    const int nwb = is_global ? B : B * nW * nW;
+    const int nwb = is_global ? B : (live_only ? B * nLW : B * nW * nW);
     const int DK = is_global ? DKg : DKw;
     const int Lkp = is_global ? GG : Lkpw;
     const int NT = is_global ? 128 : (((Lw + 15) / 16) * 16 <= 256 ? ((Lw + 15) / 16) * 16 : 128);
     // LN1 (+ window partition with zero padding)
-    SAMPT_TRY(ln_rows(c, st, x, D, is_global ? nullptr : wmap, n1w, n1b, 1e-6f, A, D * asp, (asp == 2 && p_attn == 3) ? D : 0, Mrows, D, 1));
+    SAMPT_TRY(ln_rows(c, st, x, D, is_global ? nullptr : blk_wmap, n1w, n1b, 1e-6f, A, D * asp, (asp == 2 && p_attn == 3) ? D : 0, Mrows, D, 1));
     // qkv = Linear(D, 3D)
     {
       GemmEpi ep{};
@@ -129,20 +242,20 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int H
     // x = x + proj(attn)   (window un-partition via the row map; padding rows are dropped)
     {
       GemmEpi ep{};
-      ep.out32 = x; ep.resid = x; ep.bias = projb; ep.ldc = D; ep.rowmap = is_global ? nullptr : wmap;
+      ep.out32 = x; ep.resid = x; ep.bias = projb; ep.ldc = D; ep.rowmap = is_global ? nullptr : blk_wmap;
       SAMPT_TRY(gemm_tc(c, st, att, D * asp, wproj, D * bsp, Mrows, D, D, make_seg(p_attn, D), ep));
     }
     // x = x + lin2(gelu(lin1(LN2(x))))
-    SAMPT_TRY(ln_rows(c, st, x, D, nullptr, n2w, n2b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mtok, D, 1));
+    SAMPT_TRY(ln_rows(c, st, x, D, live_only ? tmap_c : nullptr, n2w, n2b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mmlp, D, 1));
     {
       GemmEpi ep{};
       ep.out16 = hbuf; ep.bias = l1b; ep.ldc = 4 * D * asp; ep.act = 1; ep.split_off = asp == 2 ? 4 * D : 0;
-      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wl1, D * bsp, Mtok, 4 * D, D, make_seg(precision, D), ep));
+      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wl1, D * bsp, Mmlp, 4 * D, D, make_seg(precision, D), ep));
     }
     {
       GemmEpi ep{};
-      ep.out32 = x; ep.resid = x; ep.bias = l2b; ep.ldc = D;
-      SAMPT_TRY(gemm_tc(c, st, hbuf, 4 * D * asp, wl2, 4 * D * bsp, Mtok, D, 4 * D, make_seg(precision, 4 * D), ep));
+      ep.out32 = x; ep.resid = x; ep.bias = l2b; ep.ldc = D; ep.rowmap = live_only ? tmap_c : nullptr;
+      SAMPT_TRY(gemm_tc(c, st, hbuf, 4 * D * asp, wl2, 4 * D * bsp, Mmlp, D, 4 * D, make_seg(precision, 4 * D), ep));
     }
     if (is_global) {
       if (interm && gi == 0)
@@ -194,6 +307,21 @@ extern "C" int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B
   VitDims d{depth, embed_dim, num_heads, window_size, img_size / patch_size, patch_size, out_chans};
   return vit_forward(c, reinterpret_cast<cudaStream_t>(stream), resized_u8, B, Hr, Wr, d, global_idx_host, n_global, precision,
                      pixel_mean_host, pixel_std_host, features, interm);
+}
+
+// drop the saved image-independent ViT rows (must be called whenever the image-encoder weights are re-registered)
+extern "C" int sampt_vit_cache_clear(sampt_ctx* ctx) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  for (auto it = c->owned.begin(); it != c->owned.end();) {
+    if (it->first.compare(0, 9, "vitconst:") == 0) {
+      SAMPT_CUDA(cudaDeviceSynchronize());
+      cudaFree(it->second.first);
+      it = c->owned.erase(it);
+    } else {
+      ++it;
+    }
+  }
+  return 0;
 }
 
 extern "C" int sampt_ctx_set_vit_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes) {

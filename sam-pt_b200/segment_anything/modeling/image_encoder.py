@@ -73,6 +73,7 @@ class ImageEncoderViT(nn.Module):
         key = (id(ctx), self.precision, tuple(p._version for p in self.parameters()), dev)
         if self._registered != key or not ctx.owns("sam.image_encoder", self):
             torch.cuda.synchronize(dev)  # nothing may still be reading the tensors this replaces
+            native.check(native.lib().sampt_vit_cache_clear(ctx.handle), "vit_cache_clear")  # rows saved for the old weights
             split_b = self.precision >= 2
             sd = self.state_dict()
             D = self.embed_dim

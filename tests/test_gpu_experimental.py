@@ -27,3 +27,14 @@ def test_attention_v2_multi_tile_shapes():
 def test_attention_v2_inside_the_encoder():
     """the ViT encoder parity tests with the global blocks routed through attn_tc_v2_kernel"""
     _run({"SAMPT_ATTN_V2": "1"}, ["tests/test_gpu_sam.py", "-k", "encoder"], timeout=600)
+
+
+def test_vit_skip_padding_windows_is_bit_identical(tmp_path):
+    """SAMPT_VIT_SKIP_PAD=1 (csrc/vit_pipeline.cu): full first encode == compacted later encodes == a run without the flag."""
+    ref = str(tmp_path / "ref.pt")
+    for env, arg in (({"SAMPT_VIT_SKIP_PAD": "0"}, ["--dump", ref]), ({"SAMPT_VIT_SKIP_PAD": "1"}, ["--compare", ref])):
+        e = dict(os.environ, **env)
+        e.pop("SAMPT_TEST_EXPERIMENTAL", None)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_vit_skip_pad.py")] + arg, cwd=ROOT, env=e, timeout=400,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-4000:]
