@@ -16,7 +16,6 @@ details that could not be verified are marked [unverified].  The in-tree pieces 
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, Optional, Tuple
 
 import numpy as np

@@ -8,7 +8,6 @@ carrying coordinates / visibilities from one window into the next); every floati
 encoder (shared with PIPS, tensor-core convolutions), pyramid, correlation gather, embeddings, UpdateFormer, updates."""
 from __future__ import annotations
 
-import math
 import os
 from ctypes import c_int
 from typing import Dict, List, Sequence, Tuple

@@ -2,10 +2,9 @@
 SURVEY Appendix A.4) whose arithmetic runs in libsampt_b200 (csrc/pips_kernels.cu, csrc/pips_pipeline.cu)."""
 from __future__ import annotations
 
-import ctypes
 import os
 from ctypes import c_float, c_int
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 import torch
 from torch import nn

@@ -3,10 +3,9 @@ kwargs per /root/reference/configs/model/sam/image_encoder/vit_base.yaml:1-16) e
 tcgen05 GEMMs + fused attention (csrc/gemm_tc.cu, attn_tc.cu, vit_kernels.cu, vit_pipeline.cu)."""
 from __future__ import annotations
 
-import ctypes
 import os
 from ctypes import c_float, c_int
-from typing import Dict, Optional, Tuple, Type
+from typing import Dict, Tuple, Type
 
 import torch
 from torch import nn

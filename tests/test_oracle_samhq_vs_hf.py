@@ -5,7 +5,6 @@ NB transformers' port up-scales the PRE-transformer image embedding (spatially t
 the transformer output (`src`); the oracle reproduces that deviation behind `hf_upscale_quirk` ONLY for this cross-check, so
 that every other HQ piece (hq token, hq MLP, compress_vit_feat, embedding_encoder, embedding_maskfeature, mask sum) is pinned.
 The upstream behaviour itself (transformer output up-scaled) is the plain-SAM path already pinned in test_oracle_sam_vs_hf."""
-import re
 
 import pytest
 import torch

@@ -2,7 +2,7 @@
 """Launch each secondary hot kernel a few times in isolation (for `ncu --set full -k regex:...`)."""
 import os
 import sys
-from ctypes import c_float, c_int
+from ctypes import c_int
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "sam-pt_b200")):
