@@ -38,3 +38,10 @@ def test_vit_skip_padding_windows_is_bit_identical(tmp_path):
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_vit_skip_pad.py")] + arg, cwd=ROOT, env=e, timeout=400,
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         assert r.returncode == 0, r.stdout[-4000:]
+
+
+def test_gemm_cta_pair_kernel():
+    """gemm_tc2_kernel (cta_group::2, csrc/gemm_tc2.cu): the GEMM unit tests and the encoder parity tests with every eligible GEMM
+    (N % 256 == 0, M >= 256) routed through the CTA-pair kernel."""
+    _run({"SAMPT_GEMM_2CTA": "1"}, ["tests/test_gpu_gemm.py"], timeout=300)
+    _run({"SAMPT_GEMM_2CTA": "1"}, ["tests/test_gpu_sam.py", "-k", "encoder"], timeout=600)
