@@ -37,4 +37,9 @@ bool attn_tc_v2_applicable(int Lk, int DK, int HD);
 int attn_tc_v2(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp, int DK,
                int HD, int nheads, __half* out, int ld_out, int split_off);
 
+// experimental persistent variant for single-tile (windowed) attention (attn_tc_v3.cu); off unless SAMPT_ATTN_V3=1
+bool attn_tc_v3_applicable(int Lk, int NT);
+int attn_tc_v3(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp, int DK,
+               int HD, int NT, int nheads, __half* out, int ld_out, int split_off);
+
 }  // namespace sampt

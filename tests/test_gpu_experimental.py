@@ -45,3 +45,10 @@ def test_gemm_cta_pair_kernel():
     (N % 256 == 0, M >= 256) routed through the CTA-pair kernel."""
     _run({"SAMPT_GEMM_2CTA": "1"}, ["tests/test_gpu_gemm.py"], timeout=300)
     _run({"SAMPT_GEMM_2CTA": "1"}, ["tests/test_gpu_sam.py", "-k", "encoder"], timeout=600)
+
+
+def test_attention_v3_single_tile_shapes():
+    """attn_tc_v3_kernel (csrc/attn_tc_v3.cu, persistent windowed attention) on the single-tile cases of the attention unit test
+    and inside the encoder."""
+    _run({"SAMPT_ATTN_V3": "1"}, ["tests/test_gpu_attention.py", "-k", "196 or 64-64"], timeout=240)
+    _run({"SAMPT_ATTN_V3": "1"}, ["tests/test_gpu_sam.py", "-k", "encoder"], timeout=600)
