@@ -52,3 +52,33 @@ def test_attention_v3_single_tile_shapes():
     and inside the encoder."""
     _run({"SAMPT_ATTN_V3": "1"}, ["tests/test_gpu_attention.py", "-k", "196 or 64-64"], timeout=240)
     _run({"SAMPT_ATTN_V3": "1"}, ["tests/test_gpu_sam.py", "-k", "encoder"], timeout=600)
+
+
+def test_c5_slice_1080p_hq_cotracker(tmp_path):
+    """BASELINE configs[4] in a 2-frame slice... promoted to the regular suite once it has been seen green on hardware:
+    1080x1920 frames, HQ-SAM ViT-H, CoTracker (padded short clip), 16 query points, against the oracle of the whole path."""
+    code = r'''
+import sys, torch
+sys.path.insert(0, "."); sys.path.insert(0, "sam-pt_b200")
+from oracle import cotracker_ref as R, sam_ref, sampt_ref
+from sampt_b200 import factory, synth
+cfg = sam_ref.VIT_H
+sam_sd = synth.condition_sam(synth.make_state_dict(sam_ref.sam_state_dict_shapes(cfg, hq=True), 47))
+cot_sd = synth.condition_cotracker(synth.make_state_dict(R.cotracker_state_dict_shapes(), 31))
+video = synth.make_video_dict(2, 1080, 1920, 16, seed=13)
+ref = sampt_ref.sampt_forward(None, sam_ref.RefSamPredictor(sam_sd, cfg, hq=True), video, positive_points_per_mask=16,
+                              sam_iou_threshold=-1e9, iterative_refinement_iterations=2,
+                              tracker=lambda im, q: R.cotracker_point_tracker_forward(cot_sd, im, q))
+model = factory.build_sam_pt("vit_h", sam_sd, None, positive_points_per_mask=16, sam_iou_threshold=-1e9, hq=True,
+                             iterative_refinement_iterations=2, cotracker_state_dict=cot_sd)
+out = model(video)
+terr = (out["trajectories"].cpu() - ref["trajectories"]).abs().max().item()
+ious = []
+for f in range(2):
+    a, b = out["logits"][0][f].cpu() > 0, ref["logits"][0][f] > 0
+    ious.append(((a & b).sum().item()) / max((a | b).sum().item(), 1))
+print("C5 slice: max |dcoord| =", terr, "IoU =", ious)
+assert terr < 1e-2 and min(ious) >= 0.999
+'''
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, timeout=1500, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-4000:]
