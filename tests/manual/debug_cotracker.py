@@ -1,10 +1,10 @@
 """GPU bring-up aid for csrc/cotracker.cu: compares the workspace intermediates of one CoTracker window with the oracle's.
-Test infrastructure (imports oracle/); run on the GPU box:  python tools/debug_cotracker.py"""
+Test infrastructure (imports oracle/); run on the GPU box:  python tests/manual/debug_cotracker.py"""
 import os
 import sys
 from ctypes import c_int
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "sam-pt_b200"))
 import torch
