@@ -36,8 +36,10 @@ CONFIGS = {
     "C2b": (50, 480, 854, "vit_b", 8),
     "C2p": (4, 480, 854, "vit_h", 8),   # profiling-sized slice of C2 (ncu launch lists)
     "C3": (50, 480, 854, "vit_h", 64),  # BASELINE configs[2]: CoTracker (window 8), 64 query points
+    "C5": (100, 1080, 1920, "vit_h", 256),  # BASELINE configs[4]: HQ-SAM ViT-H + CoTracker, 256 points (HBM-pressure stress)
 }
-TRACKER = {"C3": "cotracker"}           # every other config tracks with PIPS
+TRACKER = {"C3": "cotracker", "C5": "cotracker"}   # every other config tracks with PIPS
+HQ_SAM = {"C5"}                                    # configs that use segment_anything_hq (MaskDecoderHQ + early ViT features)
 SAM_SEED, PIPS_SEED = 7202, 7201
 
 
@@ -97,11 +99,11 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_weights(vit):
+def make_weights(vit, hq=False):
     """Seeded synthetic checkpoints, shapes taken from the product modules themselves (same tables as the oracle's)."""
     from sampt_b200 import factory, synth
     from sam_pt.point_tracker.pips.pips import _pips_shapes
-    sam = factory.build_sam(vit)
+    sam = factory.build_sam(vit, hq=hq)
     shapes = {k: tuple(v.shape) for k, v in sam.state_dict().items()}
     sam_sd = synth.condition_sam(synth.make_state_dict(shapes, SAM_SEED))
     pips_sd = synth.condition_pips(synth.make_state_dict(_pips_shapes(8), PIPS_SEED))
@@ -120,7 +122,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     T, H, W, vit, P = CONFIGS[args.config]
-    sam_sd, pips_sd = make_weights(vit)
+    hq = args.config in HQ_SAM
+    sam_sd, pips_sd = make_weights(vit, hq=hq)
     tmp = tempfile.mkdtemp(prefix="sampt_bench_")
     ckpt = synth.write_pips_checkpoint_dir(pips_sd, os.path.join(tmp, "pips"))
     tracker = TRACKER.get(args.config, "pips")
@@ -129,7 +132,9 @@ def run_ours(args):
         from sam_pt.point_tracker.cotracker.cotracker import cotracker_shapes
         cot_sd = synth.condition_cotracker(synth.make_state_dict(cotracker_shapes(), PIPS_SEED + 1))
         args.no_cpu_baseline = True  # the CPU arm below times the PIPS path; C3 reports GPU numbers only
-    model = factory.build_sam_pt(vit, sam_sd, ckpt, positive_points_per_mask=P, sam_iou_threshold=-1e9, device=dev,
+        if world > 1:
+            args.mgpu_mode = "clip_per_gpu"  # the frame-sharded exchange is built for PIPS features
+    model = factory.build_sam_pt(vit, sam_sd, ckpt, positive_points_per_mask=P, sam_iou_threshold=-1e9, device=dev, hq=hq,
                                  cotracker_state_dict=cot_sd)
     model.sam_predictor.model.image_encoder.precision = args.precision
     model.encoder_batch = args.encoder_batch
@@ -211,7 +216,7 @@ def run_ours(args):
             "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split (3 passes MLP, 2 passes qkv/proj)", 4: "f16 hi+lo split x3 (~fp32)"}[args.precision]
                      + " ViT; f32 PIPS + decoder",
             "data": "synthetic",
-            "config": {"workload": f"{args.config}: {T} frames {H}x{W}, SAM {vit} + {'CoTracker (S=8, stride 4, interp 384x512)' if tracker == 'cotracker' else 'PIPS (S=8, stride 4)'}, 1 mask x {P} points, "
+            "config": {"workload": f"{args.config}: {T} frames {H}x{W}, {'HQ-' if hq else ''}SAM {vit} + {'CoTracker (S=8, stride 4, interp 384x512)' if tracker == 'cotracker' else 'PIPS (S=8, stride 4)'}, 1 mask x {P} points, "
                                    f"12 refinement iterations, random-init conditioned weights",
                        "clips_per_step": world, "parallelism": f"clip-per-GPU x{world}" if world > 1 else "single GPU",
                        "l2": "flushed between timed iterations (256 MiB write)", "vit_precision_passes": args.precision,
