@@ -166,6 +166,30 @@ int sampt_cotracker_window(sampt_ctx* ctx, const float* fmaps, const float* l1, 
                            const float* time_emb, int N, int iters, int time_depth, int space_depth, float* vis_out,
                            void* stream);
 
+/* ---- the callers / data formats either side of the hot path ------------------------------------------- */
+/* Query points from masks (sam_pt/utils/query_points.py:64-104 -> sklearn_extra.cluster.KMedoids(n_clusters=k).fit(px)
+ * .cluster_centers_, un-vendored scikit-learn-extra; defaults metric="euclidean", method="alternate", init="heuristic").
+ * Phase 1: pts [n,2] float32 (y,x), n <= 2048 -> D [n,n] float32 (sklearn pairwise_distances arithmetic) and rowsum [n]
+ * (numpy float32 pairwise-summation order).  The caller picks the k initial medoids from `rowsum` with numpy's own
+ * argpartition (the package's "heuristic" init; its tie order is implementation-defined), then
+ * Phase 2: the whole alternate loop on the device (one CTA, no host round trips): medoids [k] int32 IN (initial) / OUT
+ * (converged), scratch_i [2n] int32, scratch_f [n] float32, n_iter [1] int32 = iterations executed. */
+int sampt_kmedoids_distances(sampt_ctx* ctx, const float* pts, int n, float* D, float* rowsum, void* stream);
+int sampt_kmedoids_iterate(sampt_ctx* ctx, const float* D, int n, int k, int max_iter, int* medoids, int* scratch_i,
+                           float* scratch_f, int* n_iter, void* stream);
+/* Tail of the VOS harness (sam_pt/vos_eval/eval.py:304-355) fused into one kernel: background channel of zero logits, -1e8
+ * before each object's query frame gt_ti[i], ground-truth overwrite (nearest resize of gt_masks [M,Hg,Wg]) on it, softmax over
+ * the 1+M channels, bilinear up-sampling of the probabilities to (Ho,Wo) when need_resize (align_corners=False), optional
+ * horizontal flip, argmax -> uint8 index masks out [T,Ho,Wo].  logits [M,T,H,W] float32 (SamPt.forward's output). */
+int sampt_vos_index_masks(sampt_ctx* ctx, const float* logits, int M, int T, int H, int W, const float* gt_masks, int Hg,
+                          int Wg, const int* gt_ti, int Ho, int Wo, int need_resize, int flip, uint8_t* out, void* stream);
+/* Patch-similarity filtering of tracked points (sam_pt/modeling/sam_pt.py:597-682; use_patch_matching_filtering):
+ * frames [T,3,H,W] u8, query [N,3] = (t,x,y), traj [T,N,2]; Lab (skimage rgb2lab arithmetic, channels fed B,G,R as the
+ * reference does) patches of patch_size^2 pixels, sim [T,N] = exp(-||patch - query patch|| / (2 ps^2)); vis [T,N] float codes
+ * IN/OUT: visible & sim <= threshold -> -3 (PATCH_NON_SIMILAR), then -4 after/before the first such frame. */
+int sampt_patch_filter(sampt_ctx* ctx, const uint8_t* frames, int T, int H, int W, const float* query, const float* traj,
+                       int N, int patch_size, float threshold, float* vis, float* sim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

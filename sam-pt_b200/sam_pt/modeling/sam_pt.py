@@ -57,7 +57,9 @@ class SamPt(nn.Module):
         # replay them round-robin on several streams, each with its own CUDA-graph instance / buffers
         self.decode_streams = int(os.environ.get("SAMPT_DECODE_STREAMS", "8"))
         self._dec_streams = None
-        self.outputs_on_cpu = False     # reference returns CPU tensors; keeping them on the device avoids a 82 MB copy
+        # reference contract (sam_pt.py:863-864, tracker.py:72-76): logits / trajectories / visibilities are returned on the HOST
+        # (vos_eval/eval.py:323-325 mixes them with CPU ground-truth masks).  Set False to keep the 82 MB of logits in HBM.
+        self.outputs_on_cpu = True
         self.frame_annotations = []
 
     @property
@@ -66,7 +68,7 @@ class SamPt(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, video):
-        """reference sam_pt.py:122-236 (query_points branch; query_masks needs the k-medoids sampler, §8f 'next')."""
+        """reference sam_pt.py:122-236."""
         if self.training:
             raise NotImplementedError(f"{self._get_name()} does not support training...")
         frames = video["image"]
@@ -74,20 +76,25 @@ class SamPt(nn.Module):
         # upload frame by frame (async from pinned memory) and stack ON the device: no 60 MB host-side torch.stack copy
         images_dev = torch.stack([f.to(self.device, non_blocking=True) for f in frames], dim=0)
         n_frames, channels, height, width = images_dev.shape
-        if video.get("query_masks") is not None:
-            raise NotImplementedError("query_masks (k-medoids / Shi-Tomasi point sampling, sam_pt/utils/query_points.py) is "
-                                      "outside the built hot path; pass query_points (SURVEY §8f item 1)")
-        if video.get("query_points") is None:
+        if video.get("query_masks") is not None:  # e.g. the VOS harness (sam_pt/vos_eval/eval.py:298): sample points from masks
+            assert video.get("query_points") is None
+            print("SAM-PT: Using query masks")
+            query_masks = video["query_masks"].float()
+            query_points = self.extract_query_points(images_dev, query_masks, video["query_point_timestep"])
+        elif video.get("query_points") is not None:
+            print("SAM-PT: Using query points")
+            query_points = video["query_points"]
+            # the reference also runs SAM on the query frames here (extract_query_masks, sam_pt.py:168-171) but only asserts on
+            # the result's shape (and feeds SuperGlue, which is not on this path): results-neutral, skipped
+        else:
             raise ValueError("No query points or masks provided")
-        if self.use_point_reinit or self.use_patch_matching_filtering:
-            raise NotImplementedError("point re-initialisation / patch-similarity filtering are off in the reference "
-                                      "defaults (configs/model/sam_pt.yaml:23,27) and not built (SURVEY §8f item 3)")
-        print("SAM-PT: Using query points")
-        query_points = video["query_points"]
         n_masks, n_points_per_mask, _ = query_points.shape
         self.frame_annotations = [[] for _ in range(n_frames)]
 
-        trajectories, visibilities, logits, scores, scores_per_frame = self._forward(images_dev, query_points)
+        if not self.use_point_reinit:
+            trajectories, visibilities, logits, scores, scores_per_frame = self._forward(images_dev, query_points)
+        else:
+            trajectories, visibilities, logits, scores, scores_per_frame = self._forward_w_reinit(images_dev, query_points)
 
         target_hw = tuple(int(v) for v in video["target_hw"])
         resize_factor = torch.tensor(target_hw) / torch.tensor(logits.shape[-2:])
@@ -105,6 +112,50 @@ class SamPt(nn.Module):
             logits, trajectories, visibilities = logits.cpu(), trajectories.cpu(), visibilities.cpu()
         return {"logits": [m for m in logits], "scores": scores.tolist(), "scores_per_frame": scores_per_frame.tolist(),
                 "trajectories": trajectories, "visibilities": visibilities}
+
+    # ------------------------------------------------------------------------------------------------ queries from masks
+    def extract_query_points(self, images, query_masks, query_points_timestep):
+        """reference sam_pt.py:238-285: positive (and negative) query points sampled from the query masks.
+        images (T,3,H,W) uint8, query_masks (M,H,W) {0,1} float, query_points_timestep (M,) -> (M, P, 3) = (t, x, y) on the
+        device.  The masks are moved to the device: the k-medoids run there (sam_pt/utils/query_points.py)."""
+        dev = self.device
+        query_masks = query_masks.to(dev)
+        query_points_timestep = query_points_timestep.to(dev).float()
+        query_points_xy = SamPt._extract_query_points_xy(images, query_masks, query_points_timestep,
+                                                         self.positive_point_selection_method, self.positive_points_per_mask)
+        if self.negative_points_per_mask > 0:
+            negative_query_masks = [1 - qm for qm in query_masks]
+            negative_xy = SamPt._extract_query_points_xy(images, negative_query_masks, query_points_timestep,
+                                                         self.negative_point_selection_method, self.negative_points_per_mask)
+            query_points_xy = [torch.cat(x, dim=0) for x in zip(query_points_xy, negative_xy)]
+        query_points_xy = torch.stack(query_points_xy, dim=0)
+        t = query_points_timestep[:, None, None].repeat(1, query_points_xy.shape[1], 1)
+        return torch.concat([t, query_points_xy], dim=2)
+
+    @staticmethod
+    def _extract_query_points_xy(images, query_masks, query_points_timestep, point_selection_method, points_per_mask):
+        """reference sam_pt.py:287-306"""
+        from sam_pt.utils.query_points import (extract_corner_points, extract_kmedoid_points, extract_mixed_points,
+                                               extract_random_mask_points)
+        if point_selection_method == "kmedoids":
+            return [extract_kmedoid_points(qm, points_per_mask) for qm in query_masks]
+        if point_selection_method == "shi-tomasi":
+            return [extract_corner_points(images[int(t.item()), :, :, :], qm, points_per_mask)
+                    for qm, t in zip(query_masks, query_points_timestep)]
+        if point_selection_method == "random":
+            return [extract_random_mask_points(qm, points_per_mask) for qm in query_masks]
+        if point_selection_method == "mixed":
+            return extract_mixed_points(query_masks, query_points_timestep, images, points_per_mask)
+        raise NotImplementedError(f"Point selection method {point_selection_method} not implemented")
+
+    def extract_query_masks(self, images, query_points):
+        """reference sam_pt.py:308-335: SAM applied to the query points on their query frames -> (M, H, W) bool.
+        (As in the reference, every mask's points prompt frame-slot 0 of a one-frame 'clip' per mask.)"""
+        frames = torch.stack([images[int(t.item())] for t in query_points[:, 0, 0]], dim=0).to(self.device)
+        qp = query_points.to(self.device)
+        # trajectories (n_frames = M, n_masks = 1, P, 2): frame slot i holds mask i's query frame and query points
+        _, logits, _ = self._apply_sam_to_trajectories(frames, qp[:, None, :, 1:].contiguous(), torch.ones_like(qp[:, None, :, 0]))
+        return (logits > self.sam_predictor.model.mask_threshold)[0]
 
     def _forward(self, images, query_points):
         pre = self._start_encoder(images) if self.overlap_streams else None
@@ -150,14 +201,146 @@ class SamPt(nn.Module):
             m = q.shape[0]
             with torch.no_grad():
                 traj, vis = self.point_tracker.to(self.device)(rgbs.unsqueeze(0), q.reshape(1, m * points_per_mask, 3))
-            traj = traj[0].reshape(-1, m, points_per_mask, 2)
-            vis = vis[0].float().reshape(-1, m, points_per_mask)
+            traj, vis = traj[0], vis[0].float()
+            if self.use_patch_matching_filtering:
+                vis = self._patch_filter(rgbs, q.reshape(m * points_per_mask, 3), traj, vis)
+            traj = traj.reshape(-1, m, points_per_mask, 2)
+            vis = vis.reshape(-1, m, points_per_mask)
             out = float(PointVisibilityType.OUTSIDE_FRAME.value)
             oob = (traj[..., 0] / w < 0.01) | (traj[..., 1] / h < 0.01) | (traj[..., 0] / w > 0.99) | (traj[..., 1] / h > 0.99)
             vis = torch.where(oob, torch.full_like(vis, out), vis)
             trajs.append(traj)
             viss.append(vis)
         return torch.cat(trajs, dim=1), torch.cat(viss, dim=1)
+
+    def _patch_filter(self, rgbs, query_points, traj, vis):
+        """reference sam_pt.py:643-682: Lab patch similarity between every tracked position and its query patch; visible points
+        whose similarity is <= patch_similarity_threshold become PATCH_NON_SIMILAR, and everything after (before) the first
+        such frame in the forward (backward) direction REJECTED_AFTER_PATCH_WAS_NON_SIMILAR.  One native call
+        (csrc/patch_filter.cu); rgbs (T,3,H,W) uint8, query_points (N,3), traj (T,N,2), vis (T,N) float -> vis (T,N)."""
+        from ctypes import c_float, c_int
+        from sampt_b200 import native
+        T, _, H, W = rgbs.shape
+        N = query_points.shape[0]
+        vis = vis.contiguous().clone()
+        sim = torch.empty((T, N), device=rgbs.device, dtype=torch.float32)
+        ctx = native.get_context(rgbs.device)
+        native.check(native.lib().sampt_patch_filter(
+            ctx.handle, native.ptr(rgbs.contiguous()), c_int(T), c_int(H), c_int(W), native.ptr(query_points.float().contiguous()),
+            native.ptr(traj.float().contiguous()), c_int(N), c_int(int(self.patch_size)), c_float(float(self.patch_similarity_threshold)),
+            native.ptr(vis), native.ptr(sim), native.stream_ptr()), "patch_filter")
+        self._last_patch_similarities = sim
+        return vis
+
+    # ------------------------------------------------------------------------------------------------ re-initialisation
+    def _forward_w_reinit(self, images, query_points):
+        """reference sam_pt.py:355-410: forward pass with point re-initialisation from SAM's own masks, run left-to-right and on
+        the time-flipped clip, stitched per mask at its query frame.  Control flow as the reference; every tensor on the device."""
+        n_frames = images.shape[0]
+        query_points = query_points.to(self.device)
+        traj_r, vis_r, logits_r, _, spf_r = self._forward_w_reinit_inner(images, query_points)
+        qf = query_points.clone()
+        qf[:, :, 0] = n_frames - query_points[:, :, 0] - 1
+        traj_l, vis_l, logits_l, _, spf_l = self._forward_w_reinit_inner(images.flip(0), qf)
+        traj_l, vis_l, logits_l = traj_l.flip(0), vis_l.flip(0), logits_l.flip(1)
+        # NB the reference does not flip scores_per_frame of the flipped pass (sam_pt.py:386-388,401-402): reproduced
+        ts = query_points[:, 0, 0].int().tolist()
+        trajectories = torch.full_like(traj_r, torch.nan)
+        visibilities = torch.full_like(vis_r, False)
+        logits = torch.full_like(logits_r, torch.nan)
+        scores_per_frame = torch.full_like(spf_r, torch.nan)
+        for m, t in enumerate(ts):
+            trajectories[t:, m], trajectories[:t, m] = traj_r[t:, m], traj_l[:t, m]
+            visibilities[t:, m], visibilities[:t, m] = vis_r[t:, m], vis_l[:t, m]
+            logits[m, t:], logits[m, :t] = logits_r[m, t:], logits_l[m, :t]
+            scores_per_frame[t:, m], scores_per_frame[:t, m] = spf_r[t:, m], spf_l[:t, m]
+        assert not torch.isnan(trajectories).any()
+        assert not torch.isnan(logits).any()
+        scores = scores_per_frame.nanmean(dim=0)
+        return trajectories, visibilities, logits, scores, scores_per_frame
+
+    def _forward_w_reinit_inner(self, images, query_points):
+        """reference sam_pt.py:412-543."""
+        n_frames, _, height, width = images.shape
+        n_masks, points_per_mask, _ = query_points.shape
+        assert self.reinit_point_tracker_horizon >= self.reinit_horizon
+        dev = self.device
+        trajectories = torch.full((n_frames, n_masks, points_per_mask, 2), torch.nan, dtype=torch.float32, device=dev)
+        visibilities = torch.full((n_frames, n_masks, points_per_mask), False, dtype=torch.float32, device=dev)
+        scores_per_frame = torch.full((n_frames, n_masks), torch.nan, dtype=torch.float32, device=dev)
+        logits = torch.full((n_masks, n_frames, height, width), torch.nan, dtype=torch.float32, device=dev)
+        current_query_points = query_points.clone()
+        for start_frame in range(int(query_points[:, 0, 0].int().min().item()), n_frames):
+            end_frame = min(start_frame + self.reinit_horizon, n_frames)
+            end_frame_tracker = min(start_frame + self.reinit_point_tracker_horizon, n_frames)
+            current_timesteps = current_query_points[:, 0, 0].int()
+            tracked = current_timesteps == start_frame
+            if tracked.sum() == 0:
+                continue
+            query_points_i = current_query_points[tracked].clone()
+            query_points_i[:, :, 0] -= start_frame
+            assert (query_points_i[:, :, 0] == 0).all()
+            traj_i, vis_i = self._track_points(images[start_frame:end_frame_tracker], query_points_i)
+            traj_i, vis_i = traj_i[:self.reinit_horizon], vis_i[:self.reinit_horizon]
+            _, logits_i, spf_i = self._apply_sam_to_trajectories(images[start_frame:end_frame], traj_i, vis_i)
+            logits_i = logits_i.type(torch.float32)
+            logits[tracked, start_frame:end_frame] = logits_i
+            pred_masks = logits_i > 0
+            trajectories[start_frame:end_frame, tracked] = traj_i
+            visibilities[start_frame:end_frame, tracked] = vis_i
+            scores_per_frame[start_frame:end_frame, tracked] = spf_i
+            if end_frame == n_frames:
+                continue
+            area = pred_masks[:, 1:, :, :].sum([2, 3]).float()
+            area[area <= 25] = torch.nan
+            if self.reinit_horizon // 4 < area.shape[1]:
+                area[:, :self.reinit_horizon // 4] = torch.nan
+            if self.reinit_variant == "reinit-on-horizon-and-sync-masks":
+                next_timestep = self.reinit_horizon - 1 - 1
+                other = current_timesteps[current_timesteps > start_frame]
+                if len(other) > 0:
+                    next_timestep = min(next_timestep, int(other.min().item()) - start_frame - 1)
+                qts = torch.full((pred_masks.shape[0],), next_timestep, dtype=torch.int64, device=dev)
+            elif self.reinit_variant == "reinit-at-median-of-area-diff":
+                # host nanmedian: which index is returned among equal medians is the CPU implementation's (the reference runs it there)
+                qts = area.cpu().nanmedian(dim=1).indices.to(dev)
+            elif self.reinit_variant == "reinit-on-similar-mask-area":
+                target = pred_masks[:, 0, :, :].sum([1, 2])
+                diff = torch.abs(area - target[:, None])
+                diff[diff.isnan()] = torch.inf
+                qts = diff.argmin(dim=1)
+            elif self.reinit_variant == "reinit-on-similar-mask-area-and-sync-masks":
+                target = pred_masks[:, 0, :, :].sum([1, 2])
+                diff = torch.abs(area - target[:, None]) / target[:, None]
+                diff[diff.isnan()] = 720
+                per_frame = diff.sum(dim=0)
+                other = current_timesteps[current_timesteps > start_frame]
+                if len(other) > 0:
+                    per_frame[int(other.min().item()) - start_frame - 1] -= 36
+                qts = torch.full((pred_masks.shape[0],), int(per_frame.argmin(dim=0).item()), dtype=torch.int64, device=dev)
+            else:
+                raise ValueError(f"Unknown reinit variant: {self.reinit_variant}")
+            print(f"Horizon: {self.reinit_horizon}, Tracking horizon: {self.reinit_point_tracker_horizon}, "
+                  f"    Next Timesteps: {qts.tolist()} / {self.reinit_horizon - 1 - 1}")
+            ar = torch.arange(len(qts), device=dev)
+            invalid = area[ar, qts] <= 0            # (False for NaN areas, exactly as the reference's comparison, sam_pt.py:505)
+            if (~invalid).sum() > 0:
+                qmasks = pred_masks[:, 1:, :, :][ar, qts].type(torch.float32)
+                update = self.extract_query_points(images[start_frame + 1:end_frame], qmasks[~invalid], qts[~invalid].float())
+                valid_tracked = tracked.clone()
+                valid_tracked[tracked] = ~invalid
+                current_query_points[valid_tracked] = update.to(current_query_points.device)
+                current_query_points[valid_tracked, :, 0] += start_frame + 1
+            if invalid.sum() > 0:
+                invalid_tracked = tracked.clone()
+                invalid_tracked[tracked] = invalid
+                current_query_points[invalid_tracked, :, 0] = n_frames
+                current_query_points[invalid_tracked, :, 1:] = 0
+                trajectories[end_frame:, invalid_tracked] = -72
+                visibilities[end_frame:, tracked] = float(PointVisibilityType.REINIT_FAILED.value)
+                logits[invalid_tracked, end_frame:] = -float("inf")
+        scores = scores_per_frame.nanmean(dim=1)
+        return trajectories, visibilities, logits, scores, scores_per_frame
 
     # ------------------------------------------------------------------------------------------------ SAM
     @torch.no_grad()

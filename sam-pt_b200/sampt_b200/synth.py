@@ -157,12 +157,15 @@ def write_pips_checkpoint_dir(sd: Dict[str, torch.Tensor], path: str, step: int 
     return path
 
 
-def condition_cotracker(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+def condition_cotracker(sd: Dict[str, torch.Tensor], vis_bias: float = -0.9) -> Dict[str, torch.Tensor]:
     """Random-weight CoTracker is chaotic: the flow embedding carries frequencies up to ~970 rad per feature pixel, so with an
     untrained O(1) coordinate head any 1e-6 perturbation saturates at ~0.6 px after 18 iterations (measured on the oracle
     itself).  Scaling the two coordinate rows of the UpdateFormer's flow head by 0.003 (and the feature rows by 0.1) makes the
     iteration contractive like the trained checkpoint (1e-5 relative feature noise -> 2e-5 px), which is what a parity test needs.
-    A visibility bias spreads sigmoid(vis) around the reference's 0.7 threshold (configs/model/point_tracker/cotracker.yaml:7)."""
+    A visibility bias spreads sigmoid(vis) around the reference's 0.7 threshold (configs/model/point_tracker/cotracker.yaml:7):
+    the random-weight visibility logits sit at -0.2 +- 0.5 (measured on the C3 clip), so `vis_bias=-0.9` (unit tests: exercises the
+    invisible / fill-in paths) leaves almost every point invisible, while `vis_bias=+0.6` (the full-clip C3 / C5 configurations)
+    puts ~90 % of the points above the threshold, with a tail of occluded ones, so that the mask decoder actually runs."""
     sd = dict(sd)
     w, b = sd["updateformer.flow_head.weight"].clone(), sd["updateformer.flow_head.bias"].clone()
     w[:2] *= 0.003
@@ -170,5 +173,5 @@ def condition_cotracker(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     w[2:] *= 0.1
     b[2:] *= 0.1
     sd["updateformer.flow_head.weight"], sd["updateformer.flow_head.bias"] = w, b
-    sd["vis_predictor.0.bias"] = sd["vis_predictor.0.bias"] - 0.9
+    sd["vis_predictor.0.bias"] = sd["vis_predictor.0.bias"] + vis_bias
     return sd

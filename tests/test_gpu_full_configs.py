@@ -1,0 +1,93 @@
+"""Full-size parity of the BASELINE configurations against the committed full-clip goldens (tests/golden/<config>_full.npz,
+produced by tests/golden/make_golden_full.py: the reference's own PIPS tracker / the CoTracker restatement + the SAM oracle over
+EVERY frame of the clip).  Bars (BASELINE.json north_star): trajectories within 1e-3 px, visibilities exact, per-frame mask
+IoU >= 0.999 on every frame (frames whose golden mask is empty must be empty).  The per-frame numbers are written to
+gpurun_out/full_config_parity_<config>.json."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from sampt_b200 import factory, synth
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SAM_SEED, PIPS_SEED = 7202, 7201
+COT_VIS_BIAS = 0.6   # synth.condition_cotracker: ~90 % of the C3 / C5 query points visible (see its docstring)
+
+
+def _load(config):
+    z = np.load(os.path.join(HERE, "golden", f"{config}_full.npz"))
+    meta = json.load(open(os.path.join(HERE, "golden", f"{config}_full_cpu.json")))
+    return z, meta
+
+
+def _shapes(sam):
+    return {k: tuple(v.shape) for k, v in sam.state_dict().items()}
+
+
+def _run_and_compare(config, tmp_path, traj_tol=1e-3, iou_bar=0.999):
+    z, meta = _load(config)
+    T, H, W, P, hq = meta["keep"], meta["H"], meta["W"], meta["P"], meta["hq"]
+    sam_sd = synth.condition_sam(synth.make_state_dict(_shapes(factory.build_sam("vit_h", hq=hq)), SAM_SEED))
+    video = synth.make_video_dict(meta["T"], H, W, P, seed=meta["seed"])
+    video["image"] = video["image"][:T]
+    assert np.array_equal(video["query_points"].numpy(), z["query_points"])
+    if meta["tracker"] == "pips":
+        from sam_pt.point_tracker.pips.pips import _pips_shapes
+        pips_sd = synth.condition_pips(synth.make_state_dict(_pips_shapes(8), PIPS_SEED))
+        ckpt = synth.write_pips_checkpoint_dir(pips_sd, str(tmp_path / "pips"))
+        model = factory.build_sam_pt("vit_h", sam_sd, ckpt, positive_points_per_mask=P, sam_iou_threshold=-1e9, hq=hq)
+    else:
+        from sam_pt.point_tracker.cotracker.cotracker import cotracker_shapes
+        cot_sd = synth.condition_cotracker(synth.make_state_dict(cotracker_shapes(), PIPS_SEED + 1), vis_bias=COT_VIS_BIAS)
+        model = factory.build_sam_pt("vit_h", sam_sd, None, positive_points_per_mask=P, sam_iou_threshold=-1e9, hq=hq,
+                                     cotracker_state_dict=cot_sd)
+    out = model(video)
+    traj, vis = out["trajectories"].cpu().numpy(), out["visibilities"].cpu().numpy()
+    terr = float(np.abs(traj - z["trajectories"]).max())
+    vis_equal = bool(np.array_equal(vis, z["visibilities"]))
+    M = len(out["logits"])
+    ious, empties = [], 0
+    for m in range(M):
+        got = (out["logits"][m].cpu() > 0).numpy().reshape(T, -1)
+        ref = np.unpackbits(z["mask_bits"][m], axis=-1)[:, :H * W].astype(bool)
+        for f in range(T):
+            u = int((got[f] | ref[f]).sum())
+            if u == 0:
+                empties += 1
+                ious.append(1.0)
+            else:
+                ious.append(float((got[f] & ref[f]).sum()) / u)
+    serr = float(np.abs(np.array(out["scores_per_frame"], dtype=np.float32) - z["scores_per_frame"]).max())
+    rep = {"config": config, "frames": T, "max_traj_err_px": terr, "visibilities_equal": vis_equal, "min_iou": min(ious),
+           "mean_iou": float(np.mean(ious)), "frames_below_bar": int(sum(i < iou_bar for i in ious)), "empty_masks": empties,
+           "max_score_err": serr, "iou_per_frame": ious}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", f"full_config_parity_{config}.json"), "w"))
+    print(f"{config} full: max |dtraj| = {terr:.2e} px, vis equal = {vis_equal}, min IoU = {min(ious):.5f}, mean IoU = {np.mean(ious):.6f}")
+    assert terr < traj_tol, terr
+    assert vis_equal
+    assert min(ious) >= iou_bar, sorted(ious)[:5]
+
+
+def test_sampt_c2_full(tmp_path):
+    """BASELINE configs[1]: all 50 frames of 480x854, SAM ViT-H + PIPS, 8 points, 12 refinements."""
+    _run_and_compare("C2", tmp_path)
+
+
+def test_sampt_c3_full(tmp_path):
+    """BASELINE configs[2]: all 50 frames of 480x854, SAM ViT-H + CoTracker (S=8), 64 points."""
+    if not os.path.exists(os.path.join(HERE, "golden", "C3_full.npz")):
+        pytest.skip("C3 golden not generated")
+    _run_and_compare("C3", tmp_path)
+
+
+def test_sampt_c5_slice(tmp_path):
+    """BASELINE configs[4], first 8 frames: 1080x1920, HQ-SAM ViT-H + CoTracker, 256 points."""
+    if not os.path.exists(os.path.join(HERE, "golden", "C5s_full.npz")):
+        pytest.skip("C5 slice golden not generated")
+    _run_and_compare("C5s", tmp_path)
