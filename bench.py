@@ -228,6 +228,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": roof,
+            "roofline_attention": attn_roofline(dev) if vit == "vit_h" else None,
             "roofline_corr_gather": corr_roofline(dev),
             "cpu_baseline": cpu_base,
         }
@@ -419,6 +420,57 @@ def corr_roofline(dev, n_points=292):
     return {"bound": "hbm", "kernel": "pips_corr_only_kernel (fused correlation gather, N=%d points)" % n_points, "achieved": gbs,
             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": _ncu_traffic("pips_corr"), "ms": ms,
             "peak_source": pk["src"], "algorithmic_bytes": nbytes, "l2": "flushed before every launch"}
+
+
+def attn_roofline(dev, frames=10, nheads=16, hd=80):
+    """The north-star kernel: the ViT-H attention launches of one 10-frame encoder batch, timed in isolation with CUDA events.
+    windowed: 25 windows x 16 heads per frame, 14x14 = 196 tokens (operands pre-extended: DK = 80 + 2*14 -> 128);
+    global  : 16 heads per frame, 64x64 = 4096 tokens (DK = 80 + 2*64 -> 256).
+    Algorithmic FLOPs = 4 * L^2 * hd per (window, head): the QK^T and P.V contractions at the true head dim, without
+    the rel-pos extension columns or tile padding; `issued` counts what the tensor pipe executes (DK-wide QK^T, 128-row tiles)."""
+    from ctypes import c_int
+    from sampt_b200 import native
+    ctx = native.get_context(dev)
+    L_ = native.lib()
+    pk = _peaks()
+    out = {}
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for name, BH, L, DK, NT in (("windowed", frames * 25 * nheads, 196, 128, 208), ("global", frames * nheads, 4096, 256, 128)):
+        Lkp = ((L + 63) // 64) * 64
+        Q = (torch.randn((min(BH, 64), L, DK), generator=g) * 0.3).half().to(dev)
+        reps = (BH + Q.shape[0] - 1) // Q.shape[0]
+        Q = Q.repeat(reps, 1, 1)[:BH].contiguous()
+        K = Q.flip(0).contiguous()
+        V = torch.randn((BH, hd, Lkp), device=dev).half()
+        V[:, :, L:] = 0
+        o = torch.empty((BH // nheads * L, nheads * hd), device=dev, dtype=torch.float16)
+
+        def run():
+            native.check(L_.sampt_attention_f16(ctx.handle, native.ptr(Q), native.ptr(K), native.ptr(V), c_int(BH), c_int(L), c_int(L), c_int(Lkp),
+                                                c_int(DK), c_int(hd), c_int(NT), c_int(nheads), native.ptr(o), c_int(nheads * hd), c_int(0),
+                                                native.stream_ptr()), "attention")
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 5
+        e0.record()
+        for _ in range(n):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        alg = 4.0 * L * L * hd * BH
+        mt = ((L + 127) // 128) * 128
+        issued = 2.0 * mt * (((L + NT - 1) // NT) * NT) * (DK + hd) * BH
+        ach = alg / (ms * 1e-3) / 1e12
+        out[name] = {"bound": "tensor", "kernel": "attention (ViT-H %s, %d (window, head) units of %d tokens)" % (name, BH, L), "achieved": ach,
+                     "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                     "achieved_issued": issued / (ms * 1e-3) / 1e12, "frac_issued": issued / (ms * 1e-3) / 1e12 / pk["bf16_tflops"], "ms": ms,
+                     "algorithmic_flops": alg, "operands_bytes": int(Q.numel() * 2 * 2 + V.numel() * 2 + o.numel() * 2),
+                     "traffic": _ncu_traffic("attn_" + name), "peak_source": pk["src"] + ", burst"}
+        del Q, K, V, o
+    return out
 
 
 def gemm_roofline(model, dev, args):

@@ -137,8 +137,10 @@ int sampt_vit_cache_clear(sampt_ctx* ctx);
  * configs/model/sam/samhq_vit_huge.yaml:19-27).  sampt_sam_hq_features computes the per-frame
  * `embedding_encoder(image_embeddings) + compress_vit_feat(interm_embeddings[0])` map ([16*G*G][32], channels-last);
  * sampt_sam_set_hq_features selects it (NULL = plain SAM) for the following predict calls, whose single-mask output then
- * is mask_sam + mask_hq (hq_token_only=False). */
-int sampt_sam_hq_features(sampt_ctx* ctx, const float* feat_tok, const float* interm_tok, int G, float* out, void* stream);
+ * is mask_sam + mask_hq (hq_token_only=False).  `scratch`: caller-owned G*G*1280 floats (stream-ordered; the call never touches
+ * the shared ctx workspace, so frames may be processed concurrently on different streams). */
+int sampt_sam_hq_features(sampt_ctx* ctx, const float* feat_tok, const float* interm_tok, int G, float* scratch, float* out,
+                          void* stream);
 int sampt_sam_set_hq_features(sampt_ctx* ctx, const float* hq_features);
 
 /* ---- CoTracker point tracker (configs/model/point_tracker/cotracker.yaml; sam_pt/point_tracker/cotracker/tracker.py) ---

@@ -232,6 +232,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
 int attn_tc(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp,
             int DK, int HD, int NT, int nheads, __half* out, int ld_out, int split_off) {
+  if (attn_ws_applicable(Lk, DK, HD, NT))
+    return attn_ws(c, st, Qx, Kx, Vt, BH, Lq, Lk, Lkp, DK, HD, NT, nheads, out, ld_out, split_off);
   if (attn_tc_v2_applicable(Lk, DK, HD))
     return attn_tc_v2(c, st, Qx, Kx, Vt, BH, Lq, Lk, Lkp, DK, HD, nheads, out, ld_out, split_off);
   if (attn_tc_v3_applicable(Lk, NT))
@@ -250,11 +252,7 @@ int attn_tc(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const _
   const int NTB = (NT + 63) / 64;
   size_t smem = (size_t)p.DKB * 128 * 128 + (size_t)p.DKB * NT * 128 + (size_t)NTB * HD * 128 + (size_t)NTB * 128 * 128 + 1024 + 256;
   SAMPT_CHECK(smem <= 227 * 1024, "attn_tc: tile configuration needs %zu B of shared memory (> 227 KB)", smem);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    SAMPT_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    smem_set = 227 * 1024;
-  }
+  SAMPT_TRY(ensure_func_smem(c, "attn_tc_kernel", attn_tc_kernel, 227 * 1024));
   dim3 grid((Lq + 127) / 128, BH);
   attn_tc_kernel<<<grid, A_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
   c->launches++;

@@ -1,4 +1,4 @@
-// EXPERIMENTAL (off by default, SAMPT_ATTN_V2=1 selects it; NOT yet validated on hardware — see DESIGN.md §10):
+// ON by default (SAMPT_ATTN_V2=0 selects attn_tc_kernel); validated on hardware in round 2 (gpurun_out/exp_attention_v2_*.log):
 // software-pipelined variant of attn_tc_kernel for attention with several key tiles (the ViT's global blocks: Lk = 4096,
 // DK = 256 because the one-hot rel-pos extension adds 2 x 64 columns).
 //
@@ -273,7 +273,7 @@ attn_tc_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
 // true when the experimental kernel is enabled and applicable (several key tiles, fits shared memory)
 bool attn_tc_v2_applicable(int Lk, int DK, int HD) {
-  static const int enabled = [] { const char* e = std::getenv("SAMPT_ATTN_V2"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+  static const int enabled = [] { const char* e = std::getenv("SAMPT_ATTN_V2"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();   // validated on hardware in round 2: on unless =0
   if (!enabled || Lk <= 2 * V2_NT) return false;
   const int DKB = DK / 64;
   const size_t smem = (size_t)DKB * 128 * 128 + (size_t)DKB * V2_NT * 128 + 2 * (size_t)V2_NTB * HD * 128 + (size_t)V2_NTB * 128 * 128 + 1024 + 256;
@@ -292,11 +292,7 @@ int attn_tc_v2(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, cons
   const size_t smem = (size_t)p.DKB * 128 * 128 + (size_t)p.DKB * V2_NT * 128 + 2 * (size_t)V2_NTB * HD * 128 +
                       (size_t)V2_NTB * 128 * 128 + 1024 + 256;
   SAMPT_CHECK(smem <= 227 * 1024, "attn_tc_v2: needs %zu B of shared memory", smem);
-  static bool set = false;
-  if (!set) {
-    SAMPT_CUDA(cudaFuncSetAttribute(attn_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    set = true;
-  }
+  SAMPT_TRY(ensure_func_smem(c, "attn_tc_v2_kernel", attn_tc_v2_kernel, 227 * 1024));
   dim3 grid((Lq + 127) / 128, BH);
   attn_tc_v2_kernel<<<grid, V2_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
   c->launches++;

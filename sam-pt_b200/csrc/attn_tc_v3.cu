@@ -1,4 +1,4 @@
-// EXPERIMENTAL (off by default, SAMPT_ATTN_V3=1 selects it; NOT yet validated on hardware — see DESIGN.md §10):
+// ON by default (SAMPT_ATTN_V3=0 selects attn_tc_kernel); validated on hardware in round 2 (gpurun_out/exp_attention_v3.log):
 // persistent, software-pipelined variant of attn_tc_kernel for SINGLE-tile attention (the ViT's 14x14 windowed blocks:
 // Lq = Lk = 196, one 208-key tile).
 //
@@ -242,7 +242,7 @@ attn_tc_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 bool attn_tc_v3_applicable(int Lk, int NT) {
-  static const int enabled = [] { const char* e = std::getenv("SAMPT_ATTN_V3"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+  static const int enabled = [] { const char* e = std::getenv("SAMPT_ATTN_V3"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();   // validated on hardware in round 2: on unless =0
   return enabled && Lk <= NT;
 }
 
@@ -261,11 +261,7 @@ int attn_tc_v3(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, cons
   const int NTB = (NT + 63) / 64;
   const size_t smem = (size_t)p.DKB * 128 * 128 + (size_t)p.DKB * NT * 128 + (size_t)NTB * HD * 128 + (size_t)NTB * 128 * 128 + 1024 + 256;
   SAMPT_CHECK(smem <= 227 * 1024, "attn_tc_v3: needs %zu B of shared memory", smem);
-  static bool set = false;
-  if (!set) {
-    SAMPT_CUDA(cudaFuncSetAttribute(attn_tc_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    set = true;
-  }
+  SAMPT_TRY(ensure_func_smem(c, "attn_tc_v3_kernel", attn_tc_v3_kernel, 227 * 1024));
   const int grid = std::min(p.n_items, c->num_sms);
   attn_tc_v3_kernel<<<grid, V3_THREADS, smem, st>>>(tmQ, tmK, tmV, p);
   c->launches++;

@@ -73,10 +73,16 @@ struct Ctx {
   size_t dec_bytes = 0, dec_off = 0;
   cudaStream_t cap_stream = nullptr;
   std::map<std::vector<int>, void*> graph_cache;
+  std::map<int, void*> dec_slots;   // per decode slot: one buffer set carved from the slab, shared by the slot's graphs
   const float* hq_feat = nullptr;  // HQ-SAM features of the current frame (decoder.cu), caller-owned
   // library-owned device buffers that outlive a call (e.g. the ViT's image-independent padding tokens, vit_pipeline.cu);
   // freed by sampt_vit_cache_clear / sampt_ctx_destroy
   std::map<std::string, std::pair<void*, size_t>> owned;
+  // per-DEVICE lazily applied kernel attributes (cudaFuncSetAttribute is per device: a process-wide `static bool` would skip the
+  // second device of a multi-GPU process) and per-ctx scratch of the encoder pipelines
+  std::map<std::string, size_t> func_smem;
+  __half* fnet_im2col = nullptr;        // im2col operand of the tensor-core BasicEncoder path (null -> fp32 CUDA-core convs)
+  std::string fnet_prefix = "pips.";    // weight-name prefix of the encoder being run ("pips." | "cot.")
 
   const TensorRef* find(const std::string& name) const {
     auto it = tensors.find(name);
@@ -118,6 +124,17 @@ inline int get_f16(const Ctx* c, const std::string& name, const __half** out) {
   if (!t) { set_error("tensor '%s' is not registered", name.c_str()); return -4; }
   if (t->dtype != 1) { set_error("tensor '%s' is not float16", name.c_str()); return -4; }
   *out = reinterpret_cast<const __half*>(t->ptr);
+  return 0;
+}
+
+// raise a kernel's dynamic shared-memory limit once per ctx (= per device)
+template <typename F>
+inline int ensure_func_smem(Ctx* c, const char* key, F func, size_t bytes) {
+  auto it = c->func_smem.find(key);
+  if (it == c->func_smem.end() || it->second < bytes) {
+    SAMPT_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    c->func_smem[key] = bytes;
+  }
   return 0;
 }
 

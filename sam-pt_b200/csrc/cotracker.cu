@@ -287,8 +287,7 @@ static int attn_block(Ctx* c, cudaStream_t st, const CotBlockW& w, CotBufs& b, i
   SAMPT_TRY(sgemm_nt(c, st, b.h, CT_HID, w.qkv_w, CT_HID, w.qkv_b, nullptr, 0, b.qkv, 3 * CT_HID, M, 3 * CT_HID, CT_HID, 0));
   size_t smem = ((size_t)L * 49 * 2 + (size_t)8 * L) * sizeof(float);
   SAMPT_CHECK(smem <= 200 * 1024, "cot_attn: %d tokens per group do not fit shared memory", L);
-  static size_t set = 0;
-  if (smem > set) { SAMPT_CUDA(cudaFuncSetAttribute(cot_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = 200 * 1024; }
+  SAMPT_TRY(ensure_func_smem(c, "cot_attn_kernel", cot_attn_kernel, 200 * 1024));
   cot_attn_kernel<<<dim3(G, CT_HEADS), 256, smem, st>>>(b.qkv, b.att, L, gstride, lstride);
   c->launches++;
   SAMPT_LAUNCH_CHECK();

@@ -335,46 +335,59 @@ __global__ void attn_t2i_combine_kernel(const float* __restrict__ part, float* _
   out[(size_t)t * H * DH + h * DH + d] = a / l;
 }
 
-// image tokens attend to the (few) prompt tokens: q [N, H*DH], k/v [T, H*DH], T <= 512.  One thread per (image token, head).
+// image tokens attend to the (few) prompt tokens: q [N, H*DH], k/v [T, H*DH].  One thread per (image token, head).
+// k/v are staged through shared memory in chunks of TCH tokens (two passes: row max, then exp / sum / weighted sum), so any number
+// of prompt tokens is supported (BASELINE configs[4]: 256 query points + other objects' positives).
 template <int DH>
 __global__ void __launch_bounds__(256)
 attn_kv_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, float* __restrict__ out,
-                     int N, int T, int H, const int* skip) {
+                     int N, int T, int H, int TCH, const int* skip) {
   SKIP_RETURN(skip);
-  extern __shared__ float skv[];  // k [T][H*DH], v [T][H*DH]
+  extern __shared__ float skv[];  // k [TCH][H*DH], v [TCH][H*DH]
   const int ld = H * DH;
-  for (int i = threadIdx.x; i < T * ld; i += 256) { skv[i] = k[i]; skv[T * ld + i] = v[i]; }
-  __syncthreads();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= (long long)N * H) return;
-  const int n = (int)(idx / H), h = (int)(idx % H);
+  const bool live = idx < (long long)N * H;
+  const int n = live ? (int)(idx / H) : 0, h = live ? (int)(idx % H) : 0;
   float qv[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) qv[d] = q[(size_t)n * ld + h * DH + d];
   const float scale = 1.0f / sqrtf((float)DH);
   float mx = -INFINITY;
-  for (int t = 0; t < T; ++t) {
-    const float* kp = skv + t * ld + h * DH;
-    float s = 0.f;
+  for (int t0 = 0; t0 < T; t0 += TCH) {
+    const int nt = min(TCH, T - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt * ld; i += 256) skv[i] = k[(size_t)t0 * ld + i];
+    __syncthreads();
+    for (int t = 0; t < nt; ++t) {
+      const float* kp = skv + t * ld + h * DH;
+      float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) s = fmaf(qv[d], kp[d], s);
-    mx = fmaxf(mx, s * scale);
+      for (int d = 0; d < DH; ++d) s = fmaf(qv[d], kp[d], s);
+      mx = fmaxf(mx, s * scale);
+    }
   }
   float acc[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) acc[d] = 0.f;
   float lsum = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float* kp = skv + t * ld + h * DH;
-    float s = 0.f;
+  for (int t0 = 0; t0 < T; t0 += TCH) {
+    const int nt = min(TCH, T - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt * ld; i += 256) { skv[i] = k[(size_t)t0 * ld + i]; skv[TCH * ld + i] = v[(size_t)t0 * ld + i]; }
+    __syncthreads();
+    for (int t = 0; t < nt; ++t) {
+      const float* kp = skv + t * ld + h * DH;
+      float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) s = fmaf(qv[d], kp[d], s);
-    float p = expf(s * scale - mx);
-    lsum += p;
-    const float* vp = skv + T * ld + t * ld + h * DH;
+      for (int d = 0; d < DH; ++d) s = fmaf(qv[d], kp[d], s);
+      float p = expf(s * scale - mx);
+      lsum += p;
+      const float* vp = skv + TCH * ld + t * ld + h * DH;
 #pragma unroll
-    for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, vp[d], acc[d]);
+      for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, vp[d], acc[d]);
+    }
   }
+  if (!live) return;
   float inv = 1.0f / lsum;
 #pragma unroll
   for (int d = 0; d < DH; ++d) out[(size_t)n * ld + h * DH + d] = acc[d] * inv;
@@ -804,14 +817,10 @@ static int two_way_layer(Ctx* c, cudaStream_t st, const LayerW& L, int idx, DecB
   SAMPT_TRY(sg(c, st, b.qpe, 256, L.i2t.kw, L.i2t.kb, nullptr, 0, b.tk, 128, T, 128, 256, 0, skip));
   SAMPT_TRY(sg(c, st, b.queries, 256, L.i2t.vw, L.i2t.vb, nullptr, 0, b.tv, 128, T, 128, 256, 0, skip));
   {
-    size_t smem = (size_t)2 * T * 128 * sizeof(float);
-    SAMPT_CHECK(smem <= 200 * 1024, "too many prompt tokens (%d) for the image->token attention kernel", T);
-    static size_t set = 0;
-    if (smem > set) {
-      SAMPT_CUDA(cudaFuncSetAttribute(attn_kv_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      set = 200 * 1024;
-    }
-    attn_kv_small_kernel<16><<<cdiv((long long)GG * 8, 256), 256, smem, st>>>(b.iq, b.tk, b.tv, b.ia, GG, T, 8, skip);
+    const int TCH = std::min(T, 192);   // prompt tokens staged per pass: 2 * 192 * 128 * 4 B = 192 KB of shared memory at most
+    size_t smem = (size_t)2 * TCH * 128 * sizeof(float);
+    SAMPT_TRY(ensure_func_smem(c, "attn_kv_small_kernel<16>", attn_kv_small_kernel<16>, 200 * 1024));
+    attn_kv_small_kernel<16><<<cdiv((long long)GG * 8, 256), 256, smem, st>>>(b.iq, b.tk, b.tv, b.ia, GG, T, 8, TCH, skip);
     LAUNCH_OK();
   }
   SAMPT_TRY(sg(c, st, b.ia, 128, L.i2t.ow, L.i2t.ob, b.keys, 256, b.src, 256, GG, 256, 128, 0, skip));   // keys + attn_out
@@ -995,15 +1004,24 @@ static int enqueue_refine_chain(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, co
 }
 
 // One captured CUDA graph per chain shape: the ~500 kernels of a frame's 13 predict_torch calls replay as ONE launch.
-// The graph works on buffers carved from the decoder slab (stable addresses); inputs/outputs are staged with D2D copies.
-struct RefineGraph {
-  RefineShape shape;
+// Buffers are carved from the decoder slab (stable addresses) ONCE PER SLOT, sized for `Kcap` prompt points, and shared by
+// every graph of that slot: a slot's chains are stream-ordered (one stream per slot), so graphs that differ only in the number
+// of visible prompt points K reuse the same memory and a new K costs a capture (~ms), not another ~60 MB buffer set.
+// (Round 1 allocated a full buffer set per (K, npos, slot): a clip whose visible-point count varied filled the slab.)
+struct SlotBufs {
   DecBufs bufs;
   float *feat, *coords, *pos_coords, *logits, *iou, *low, *box, *hqfeat = nullptr;
   int *labels, *pos_labels, *n_done, *bbox, *skip;
+  int Kcap = 0, GG = 0, HW = 0, n_out_tok = 0;
+  bool hq = false;
+};
+struct RefineGraph {
+  RefineShape shape;
   cudaGraphExec_t exec = nullptr;
   long long launches = 0;
 };
+constexpr int DEC_KCAP_MIN = 320;      // 256 query points + other objects' positives (BASELINE configs[4]) without a re-carve
+constexpr size_t DEC_MAX_GRAPHS = 512;
 
 static void* dec_alloc(Ctx* c, size_t bytes) {
   size_t a = (c->dec_off + 255) & ~size_t(255);
@@ -1018,57 +1036,77 @@ static int dec_get(Ctx* c, T** out, size_t count, const char* what) {
   return 0;
 }
 
-static int build_refine_graph(Ctx* c, DecW& w, const RefineShape& s, bool hq, RefineGraph** out) {
+// drop every captured graph and every slot's buffers (nothing may be in flight: synchronises the device)
+static int dec_evict_all(Ctx* c) {
+  SAMPT_CUDA(cudaDeviceSynchronize());
+  for (auto& kv : c->graph_cache) {
+    RefineGraph* g = reinterpret_cast<RefineGraph*>(kv.second);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    delete g;
+  }
+  c->graph_cache.clear();
+  for (auto& kv : c->dec_slots) delete reinterpret_cast<SlotBufs*>(kv.second);
+  c->dec_slots.clear();
+  c->dec_off = 0;
+  return 0;
+}
+
+static int carve_slot(Ctx* c, DecW& w, const RefineShape& s, bool hq, int Kcap, SlotBufs** out) {
+  SlotBufs* sb = new SlotBufs();
+  sb->Kcap = Kcap; sb->GG = s.G * s.G; sb->HW = s.H * s.W; sb->hq = hq; sb->n_out_tok = w.n_out_tok;
+  const int GG = sb->GG, Tmax = w.n_out_tok + Kcap + 2;
+  DecBufs& b = sb->bufs;
+  int rc = 0;
+#define DG(ptr, count, what) if (rc == 0) rc = dec_get(c, &(ptr), (size_t)(count), what)
+  DG(b.tokens, Tmax * 256, "tokens"); DG(b.queries, Tmax * 256, "queries"); DG(b.qpe, Tmax * 256, "qpe"); DG(b.tq, Tmax * 256, "tq");
+  DG(b.tk, Tmax * 256, "tk"); DG(b.tv, Tmax * 256, "tv"); DG(b.ta, Tmax * 256, "ta"); DG(b.tmp, Tmax * 256, "tmp");
+  DG(b.mlp_h, (size_t)Tmax * 2048, "mlp_h");
+  DG(b.src, (size_t)GG * 256, "src"); DG(b.keys, (size_t)GG * 256, "keys"); DG(b.ik, (size_t)GG * 128, "ik"); DG(b.iv, (size_t)GG * 128, "iv");
+  DG(b.iq, (size_t)GG * 128, "iq"); DG(b.ia, (size_t)GG * 128, "ia"); DG(b.u1, (size_t)GG * 256, "u1"); DG(b.hyper, 256, "hyper");
+  if (hq) { DG(b.u_sam, (size_t)16 * GG * 32, "u_sam"); DG(b.mf1, (size_t)16 * GG * 64, "mf1"); DG(b.mf2, (size_t)16 * GG * 32, "mf2"); }
+  else { b.u_sam = b.mf1 = b.mf2 = nullptr; }
+  DG(b.iou4, 8, "iou4"); DG(b.part, (size_t)Tmax * 8 * ((GG + 255) / 256) * 18, "attn partials");
+  DG(sb->feat, (size_t)GG * 256, "feat stage"); DG(sb->coords, (size_t)Kcap * 2, "coords"); DG(sb->labels, Kcap, "labels");
+  DG(sb->pos_coords, (size_t)Kcap * 2, "pos coords"); DG(sb->pos_labels, Kcap, "pos labels");
+  DG(sb->logits, (size_t)s.H * s.W, "logits stage"); DG(sb->iou, 8, "iou"); DG(sb->low, (size_t)16 * GG, "low_res");
+  DG(sb->n_done, 8, "n_done"); DG(sb->bbox, 8, "bbox"); DG(sb->skip, 8, "skip"); DG(sb->box, 8, "box");
+  if (hq) DG(sb->hqfeat, (size_t)16 * GG * 32, "hq features stage");
+#undef DG
+  if (rc != 0) { delete sb; return rc; }
+  if (hq) SAMPT_CUDA(cudaMemset(sb->hqfeat, 0, (size_t)16 * GG * 32 * sizeof(float)));
+  *out = sb;
+  return 0;
+}
+
+static int build_refine_graph(Ctx* c, DecW& w, const RefineShape& s, SlotBufs* sb, RefineGraph** out) {
   RefineGraph* g = new RefineGraph();
   g->shape = s;
-  const int GG = s.G * s.G, Tmax = w.n_out_tok + s.K + 2;
-  DecBufs& b = g->bufs;
-  SAMPT_TRY(dec_get(c, &b.tokens, (size_t)Tmax * 256, "tokens")); SAMPT_TRY(dec_get(c, &b.queries, (size_t)Tmax * 256, "queries"));
-  SAMPT_TRY(dec_get(c, &b.qpe, (size_t)Tmax * 256, "qpe")); SAMPT_TRY(dec_get(c, &b.tq, (size_t)Tmax * 256, "tq"));
-  SAMPT_TRY(dec_get(c, &b.tk, (size_t)Tmax * 256, "tk")); SAMPT_TRY(dec_get(c, &b.tv, (size_t)Tmax * 256, "tv"));
-  SAMPT_TRY(dec_get(c, &b.ta, (size_t)Tmax * 256, "ta")); SAMPT_TRY(dec_get(c, &b.tmp, (size_t)Tmax * 256, "tmp"));
-  SAMPT_TRY(dec_get(c, &b.mlp_h, (size_t)Tmax * 2048, "mlp_h"));
-  SAMPT_TRY(dec_get(c, &b.src, (size_t)GG * 256, "src")); SAMPT_TRY(dec_get(c, &b.keys, (size_t)GG * 256, "keys"));
-  SAMPT_TRY(dec_get(c, &b.ik, (size_t)GG * 128, "ik")); SAMPT_TRY(dec_get(c, &b.iv, (size_t)GG * 128, "iv"));
-  SAMPT_TRY(dec_get(c, &b.iq, (size_t)GG * 128, "iq")); SAMPT_TRY(dec_get(c, &b.ia, (size_t)GG * 128, "ia"));
-  SAMPT_TRY(dec_get(c, &b.u1, (size_t)GG * 256, "u1")); SAMPT_TRY(dec_get(c, &b.hyper, (size_t)256, "hyper"));
-  SAMPT_TRY(dec_get(c, &b.u_sam, (size_t)16 * GG * 32, "u_sam")); SAMPT_TRY(dec_get(c, &b.mf1, (size_t)16 * GG * 64, "mf1"));
-  SAMPT_TRY(dec_get(c, &b.mf2, (size_t)16 * GG * 32, "mf2"));
-  SAMPT_TRY(dec_get(c, &b.iou4, (size_t)8, "iou4"));
-  SAMPT_TRY(dec_get(c, &b.part, (size_t)Tmax * 8 * ((GG + 255) / 256) * 18, "attn partials"));
-  SAMPT_TRY(dec_get(c, &g->feat, (size_t)GG * 256, "feat stage"));
-  SAMPT_TRY(dec_get(c, &g->coords, (size_t)std::max(1, s.K) * 2, "coords")); SAMPT_TRY(dec_get(c, &g->labels, (size_t)std::max(1, s.K), "labels"));
-  SAMPT_TRY(dec_get(c, &g->pos_coords, (size_t)std::max(1, s.npos) * 2, "pos coords"));
-  SAMPT_TRY(dec_get(c, &g->pos_labels, (size_t)std::max(1, s.npos), "pos labels"));
-  SAMPT_TRY(dec_get(c, &g->logits, (size_t)s.H * s.W, "logits stage"));
-  SAMPT_TRY(dec_get(c, &g->iou, (size_t)8, "iou")); SAMPT_TRY(dec_get(c, &g->low, (size_t)16 * GG, "low_res"));
-  SAMPT_TRY(dec_get(c, &g->n_done, (size_t)8, "n_done")); SAMPT_TRY(dec_get(c, &g->bbox, (size_t)8, "bbox"));
-  SAMPT_TRY(dec_get(c, &g->skip, (size_t)8, "skip")); SAMPT_TRY(dec_get(c, &g->box, (size_t)8, "box"));
-  RefinePtrs p{g->feat, g->coords, g->labels, g->pos_coords, g->pos_labels, g->logits, g->iou, g->low, g->n_done, g->bbox, g->skip, g->box};
-  if (hq) {
-    SAMPT_TRY(dec_get(c, &g->hqfeat, (size_t)16 * GG * 32, "hq features stage"));
-    SAMPT_CUDA(cudaMemset(g->hqfeat, 0, (size_t)16 * GG * 32 * sizeof(float)));
-    p.hq_feat = g->hqfeat;
-  }
+  DecBufs b = sb->bufs;   // copy: decode_once writes b.T
+  const int GG = sb->GG;
+  RefinePtrs p{sb->feat, sb->coords, sb->labels, sb->pos_coords, sb->pos_labels, sb->logits, sb->iou, sb->low, sb->n_done, sb->bbox,
+               sb->skip, sb->box};
+  if (sb->hq) p.hq_feat = sb->hqfeat;
   if (!c->cap_stream) SAMPT_CUDA(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
-  // eager warm-up on the capture stream (sets function attributes, touches every code path), then capture.
-  // cap_stream does not synchronise with the legacy default stream: make sure pending weight uploads have landed.
+  // eager warm-up on the capture stream (sets function attributes, touches every code path), then capture.  The slot's buffers
+  // may still be in use by an earlier graph of this slot on the caller's stream, and cap_stream does not synchronise with the
+  // legacy default stream (pending weight uploads): wait for the device.
   SAMPT_CUDA(cudaDeviceSynchronize());
-  SAMPT_CUDA(cudaMemsetAsync(g->feat, 0, (size_t)GG * 256 * sizeof(float), c->cap_stream));
-  SAMPT_CUDA(cudaMemsetAsync(g->coords, 0, (size_t)std::max(1, s.K) * 2 * sizeof(float), c->cap_stream));
-  SAMPT_CUDA(cudaMemsetAsync(g->labels, 0, (size_t)std::max(1, s.K) * sizeof(int), c->cap_stream));
-  SAMPT_CUDA(cudaMemsetAsync(g->pos_coords, 0, (size_t)std::max(1, s.npos) * 2 * sizeof(float), c->cap_stream));
-  SAMPT_CUDA(cudaMemsetAsync(g->pos_labels, 0, (size_t)std::max(1, s.npos) * sizeof(int), c->cap_stream));
+  SAMPT_CUDA(cudaMemsetAsync(sb->feat, 0, (size_t)GG * 256 * sizeof(float), c->cap_stream));
+  SAMPT_CUDA(cudaMemsetAsync(sb->coords, 0, (size_t)sb->Kcap * 2 * sizeof(float), c->cap_stream));
+  SAMPT_CUDA(cudaMemsetAsync(sb->labels, 0, (size_t)sb->Kcap * sizeof(int), c->cap_stream));
+  SAMPT_CUDA(cudaMemsetAsync(sb->pos_coords, 0, (size_t)sb->Kcap * 2 * sizeof(float), c->cap_stream));
+  SAMPT_CUDA(cudaMemsetAsync(sb->pos_labels, 0, (size_t)sb->Kcap * sizeof(int), c->cap_stream));
   const long long l0 = c->launches;
-  SAMPT_TRY(enqueue_refine_chain(c, c->cap_stream, w, b, s, p));
+  int rc = enqueue_refine_chain(c, c->cap_stream, w, b, s, p);
+  if (rc != 0) { delete g; return rc; }
   SAMPT_CUDA(cudaStreamSynchronize(c->cap_stream));
   g->launches = c->launches - l0;
   SAMPT_CUDA(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeRelaxed));
-  int rc = enqueue_refine_chain(c, c->cap_stream, w, b, s, p);
+  rc = enqueue_refine_chain(c, c->cap_stream, w, b, s, p);
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
   c->launches -= g->launches;  // the capture pass did not execute anything
-  if (rc != 0) return rc;
+  if (rc != 0) { delete g; return rc; }
   SAMPT_CHECK(e == cudaSuccess && graph != nullptr, "stream capture of the decode chain failed: %s", cudaGetErrorString(e));
   SAMPT_CUDA(cudaGraphInstantiate(&g->exec, graph, 0));
   cudaGraphDestroy(graph);
@@ -1080,12 +1118,7 @@ static int build_refine_graph(Ctx* c, DecW& w, const RefineShape& s, bool hq, Re
 
 extern "C" int sampt_ctx_set_decoder_workspace(sampt_ctx* ctx, void* dev_ptr, size_t bytes) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
-  for (auto& kv : c->graph_cache) {
-    RefineGraph* g = reinterpret_cast<RefineGraph*>(kv.second);
-    if (g->exec) cudaGraphExecDestroy(g->exec);
-    delete g;
-  }
-  c->graph_cache.clear();
+  SAMPT_TRY(dec_evict_all(c));
   c->dec_base = reinterpret_cast<char*>(dev_ptr);
   c->dec_bytes = bytes;
   c->dec_off = 0;
@@ -1102,7 +1135,8 @@ extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, i
   SAMPT_TRY(load_dec(c, &w));
   RefineShape s{G, K, n_pos_first > 0 ? n_pos_first : 0, n_refine, in_h, in_w, H, W};
   if (c->dec_base == nullptr) {
-    // eager path (no decoder slab registered): buffers from the shared workspace, kernels launched one by one
+    // eager path (no decoder slab registered): buffers from the shared workspace, kernels launched one by one.  NOT safe for
+    // concurrent use from several streams (one shared workspace): the Python side forces a single decode stream here.
     c->ws_reset();
     DecBufs b;
     SAMPT_TRY(alloc_dec_bufs(c, &b, w.n_out_tok + K + 2, G * G));
@@ -1115,51 +1149,77 @@ extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, i
     return enqueue_refine_chain(c, st, w, b, s, p);
   }
   const bool hq = w.hq && c->hq_feat != nullptr;
+  const int GG = G * G;
   // graph_slot: independent buffer sets / graph instances so that several frames' chains can replay CONCURRENTLY on
-  // different streams (each chain is a long sequence of tiny kernels: latency-, not throughput-bound)
+  // different streams (each chain is a long sequence of tiny kernels: latency-, not throughput-bound).  Contract: all calls
+  // with the same slot are issued on the same stream.
+  SlotBufs* sb = nullptr;
+  for (int attempt = 0; attempt < 2 && sb == nullptr; ++attempt) {
+    auto sit = c->dec_slots.find(graph_slot);
+    if (sit != c->dec_slots.end()) {
+      sb = reinterpret_cast<SlotBufs*>(sit->second);
+      if (sb->Kcap < K || sb->GG != GG || sb->HW < H * W || sb->hq != hq || sb->n_out_tok != w.n_out_tok) {
+        SAMPT_TRY(dec_evict_all(c));   // the slot's buffers do not fit this call: re-carve everything
+        sb = nullptr;
+        continue;
+      }
+    } else {
+      const int Kcap = std::max(DEC_KCAP_MIN, ((K + 63) / 64) * 64);
+      int rc = carve_slot(c, w, s, hq, Kcap, &sb);
+      if (rc == -3 && attempt == 0 && !c->dec_slots.empty()) { SAMPT_TRY(dec_evict_all(c)); sb = nullptr; continue; }
+      if (rc != 0) return rc;
+      c->dec_slots[graph_slot] = sb;
+    }
+  }
+  SAMPT_CHECK(sb != nullptr, "decoder slab (%zu bytes) too small for slot %d (K=%d, %dx%d)", c->dec_bytes, graph_slot, K, H, W);
   std::vector<int> key{G, K, s.npos, n_refine, in_h, in_w, H, W, w.n_out_tok, hq ? 1 : 0, graph_slot};
   RefineGraph* g = nullptr;
   auto it = c->graph_cache.find(key);
   if (it == c->graph_cache.end()) {
+    if (c->graph_cache.size() >= DEC_MAX_GRAPHS) {   // bound the number of instantiated graphs: start over
+      SAMPT_TRY(dec_evict_all(c));
+      return sampt_sam_predict_refine(ctx, feat_tok, G, coords, labels, K, pos_coords, pos_labels, n_pos_first, n_refine, in_h, in_w, H,
+                                      W, logits, iou, low_res, n_refine_done, graph_slot, stream);
+    }
     // weights may not change between capture and replay: the cache is dropped by sampt_ctx_set_decoder_workspace,
     // which the Python side calls whenever SAM's decoder weights are (re)registered
-    SAMPT_TRY(build_refine_graph(c, w, s, hq, &g));
+    SAMPT_TRY(build_refine_graph(c, w, s, sb, &g));
     c->graph_cache[key] = g;
   } else {
     g = reinterpret_cast<RefineGraph*>(it->second);
   }
-  const int GG = G * G;
-  SAMPT_CUDA(cudaMemcpyAsync(g->feat, feat_tok, (size_t)GG * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  SAMPT_CUDA(cudaMemcpyAsync(g->coords, coords, (size_t)K * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  SAMPT_CUDA(cudaMemcpyAsync(g->labels, labels, (size_t)K * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(sb->feat, feat_tok, (size_t)GG * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(sb->coords, coords, (size_t)K * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(sb->labels, labels, (size_t)K * sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (s.npos > 0) {
-    SAMPT_CUDA(cudaMemcpyAsync(g->pos_coords, pos_coords, (size_t)s.npos * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    SAMPT_CUDA(cudaMemcpyAsync(g->pos_labels, pos_labels, (size_t)s.npos * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    SAMPT_CUDA(cudaMemcpyAsync(sb->pos_coords, pos_coords, (size_t)s.npos * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SAMPT_CUDA(cudaMemcpyAsync(sb->pos_labels, pos_labels, (size_t)s.npos * sizeof(int), cudaMemcpyDeviceToDevice, st));
   }
-  if (hq) SAMPT_CUDA(cudaMemcpyAsync(g->hqfeat, c->hq_feat, (size_t)16 * GG * 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (hq) SAMPT_CUDA(cudaMemcpyAsync(sb->hqfeat, c->hq_feat, (size_t)16 * GG * 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   SAMPT_CUDA(cudaGraphLaunch(g->exec, st));
   c->launches += g->launches;
-  SAMPT_CUDA(cudaMemcpyAsync(logits, g->logits, (size_t)H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  SAMPT_CUDA(cudaMemcpyAsync(iou, g->iou, sizeof(float), cudaMemcpyDeviceToDevice, st));
-  SAMPT_CUDA(cudaMemcpyAsync(low_res, g->low, (size_t)16 * GG * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (n_refine_done) SAMPT_CUDA(cudaMemcpyAsync(n_refine_done, g->n_done, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(logits, sb->logits, (size_t)H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(iou, sb->iou, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  SAMPT_CUDA(cudaMemcpyAsync(low_res, sb->low, (size_t)16 * GG * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (n_refine_done) SAMPT_CUDA(cudaMemcpyAsync(n_refine_done, sb->n_done, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
 // HQ-SAM: per-frame `hq_features` = embedding_encoder(image_embeddings) + compress_vit_feat(interm_embeddings[0])
 // (MaskDecoderHQ.predict_masks prologue).  feat_tok [G*G,256], interm_tok [G*G,vit_dim] (output of the first global
 // attention block, token-major) -> out [16*G*G][32] channels-last low-res map.
-extern "C" int sampt_sam_hq_features(sampt_ctx* ctx, const float* feat_tok, const float* interm_tok, int G, float* out, void* stream) {
+extern "C" int sampt_sam_hq_features(sampt_ctx* ctx, const float* feat_tok, const float* interm_tok, int G, float* scratch,
+                                     float* out, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  c->ws_reset();
   DecW w;
   SAMPT_TRY(load_dec(c, &w));
   SAMPT_CHECK(w.hq, "sampt_sam_hq_features: the registered mask decoder is not an HQ decoder");
+  SAMPT_CHECK(scratch != nullptr, "sampt_sam_hq_features: caller-owned scratch of G*G*1280 floats is required");
   const int GG = G * G;
-  float *e1, *c1;
-  SAMPT_TRY(ws_get(c, &e1, (size_t)GG * 256, "hq e1"));
-  SAMPT_TRY(ws_get(c, &c1, (size_t)GG * 1024, "hq c1"));
+  // caller-owned scratch (NOT the shared ctx workspace): frames are decoded concurrently on several streams
+  float* e1 = scratch;
+  float* c1 = scratch + (size_t)GG * 256;
   SAMPT_TRY(sgemm_nt(c, st, feat_tok, 256, w.enc0_w, 256, w.enc0_b4, nullptr, 0, e1, 256, GG, 256, 256, 0));
   SAMPT_TRY(sgemm_nt(c, st, interm_tok, w.vit_dim, w.cv0_w, w.vit_dim, w.cv0_b4, nullptr, 0, c1, 1024, GG, 1024, w.vit_dim, 0));
   hq_features_kernel<<<cdiv(16 * GG, 256), 256, 0, st>>>(e1, c1, w.enc_lnw, w.enc_lnb, w.enc3_w, w.enc3_b, w.cv_lnw, w.cv_lnb, w.cv3_w,

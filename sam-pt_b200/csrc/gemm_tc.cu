@@ -210,11 +210,7 @@ int gemm_tc(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int 
   SAMPT_CHECK((ep.out16 != nullptr) != (ep.out32 != nullptr), "gemm_tc: exactly one of out16/out32 must be set");
   SAMPT_CHECK(ep.ldc % 8 == 0, "gemm_tc: ldc must be a multiple of 8");
   if (gemm_tc2_applicable(M, N, K, ep)) return gemm_tc2(c, st, A, lda, B, ldb, M, N, K, seg, ep);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SAMPT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES));
-    attr_set = true;
-  }
+  SAMPT_TRY(ensure_func_smem(c, "gemm_tc_kernel", gemm_tc_kernel, G_SMEM_BYTES));
   CUtensorMap tmA, tmB;
   // the A/B matrices may carry several K segments side by side (hi | lo): inner extent = lda / ldb
   SAMPT_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)lda, (uint64_t)M, (uint64_t)lda * 2, G_BK, G_BM));

@@ -1,4 +1,4 @@
-// EXPERIMENTAL (off by default, SAMPT_GEMM_2CTA=1 selects it; NOT yet validated on hardware — DESIGN.md §10):
+// ON by default (SAMPT_GEMM_2CTA=0 selects gemm_tc_kernel); validated on hardware in round 2 (gpurun_out/exp_gemm_cta_pair.log):
 // CTA-pair variant of gemm_tc_kernel:  C[M,N] = epilogue( A[M,K] . B[N,K]^T ) with tcgen05.mma.cta_group::2.
 //
 // Why: the 1-CTA kernel (M128 x N256 x K16 per instruction) reads 12 KB of shared memory per 128 tensor-pipe cycles while TMA
@@ -257,18 +257,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 bool gemm_tc2_applicable(int M, int N, int K, const GemmEpi& ep) {
-  static const int enabled = [] { const char* e = std::getenv("SAMPT_GEMM_2CTA"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+  static const int enabled = [] { const char* e = std::getenv("SAMPT_GEMM_2CTA"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();   // validated on hardware in round 2: on unless =0
   (void)ep;
   return enabled && N % P_BN == 0 && K % P_BK == 0 && M >= 2 * P_BM;
 }
 
 int gemm_tc2(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmSeg& seg,
              const GemmEpi& ep) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SAMPT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    attr_set = true;
-  }
+  SAMPT_TRY(ensure_func_smem(c, "gemm_tc2_kernel", gemm_tc2_kernel, P_SMEM_BYTES));
   CUtensorMap tmA, tmB;
   SAMPT_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)lda, (uint64_t)M, (uint64_t)lda * 2, P_BK, P_BM));
   SAMPT_TRY(make_tmap_2d_f16(&tmB, B, (uint64_t)ldb, (uint64_t)N, (uint64_t)ldb * 2, P_BK, P_BN / 2));

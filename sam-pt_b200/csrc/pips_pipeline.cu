@@ -27,28 +27,27 @@ static bool fnet_uses_tc(const Ctx* c, const std::string& prefix) {
   return f != nullptr && f->dims[0] == 1 && c->find(prefix + "fnet.conv2.w16") != nullptr;
 }
 
-// scratch for the tensor-core convolution path (im2col operand); null -> strict fp32 CUDA-core convolutions
-static __half* g_im2col = nullptr;
-// weight-name prefix of the encoder being run ("pips." or "cot."; the CoTracker BasicEncoder has the same architecture)
-static std::string g_prefix = "pips.";
+// c->fnet_im2col: scratch for the tensor-core convolution path (im2col operand); null -> strict fp32 CUDA-core convolutions
+// c->fnet_prefix: weight-name prefix of the encoder being run ("pips." or "cot."; the CoTracker BasicEncoder has the same
+// architecture).  Both live in the ctx (not process-wide) so that encoders of different ctxs / devices never see each other's.
 
 static int conv_by_name(Ctx* c, cudaStream_t st, const std::string& name, const Act& in, Act* out, int R, int stride, int pad) {
-  if (g_im2col != nullptr) {
+  if (c->fnet_im2col != nullptr) {
     // implicit-GEMM on tcgen05: A = im2col(in) as fp16 hi|lo, B = weights hi|lo, 3 split passes (~fp32), fp32 NHWC output
     const __half* w16; const float* b;
-    SAMPT_TRY(get_f16(c, g_prefix + name + ".w16", &w16));
-    SAMPT_TRY(get_f32(c, g_prefix + name + ".bias", &b));
+    SAMPT_TRY(get_f16(c, c->fnet_prefix + name + ".w16", &w16));
+    SAMPT_TRY(get_f32(c, c->fnet_prefix + name + ".bias", &b));
     const int K = R * R * in.c, Kp = ((K + 63) / 64) * 64;
-    SAMPT_TRY(im2col_nhwc_split(c, st, in.p, g_im2col, in.n, in.h, in.w, in.c, R, R, stride, pad, Kp));
+    SAMPT_TRY(im2col_nhwc_split(c, st, in.p, c->fnet_im2col, in.n, in.h, in.w, in.c, R, R, stride, pad, Kp));
     const int Ho = (in.h + 2 * pad - R) / stride + 1, Wo = (in.w + 2 * pad - R) / stride + 1;
     GemmSeg seg{3, {0, Kp, 0}, {0, 0, Kp}};
     GemmEpi ep{};
     ep.out32 = out->p; ep.bias = b; ep.ldc = out->c;
-    return gemm_tc(c, st, g_im2col, 2 * Kp, w16, 2 * Kp, in.n * Ho * Wo, out->c, Kp, seg, ep);
+    return gemm_tc(c, st, c->fnet_im2col, 2 * Kp, w16, 2 * Kp, in.n * Ho * Wo, out->c, Kp, seg, ep);
   }
   const float *w, *b;
-  SAMPT_TRY(get_f32(c, g_prefix + name + ".weight_rsck", &w));
-  SAMPT_TRY(get_f32(c, g_prefix + name + ".bias", &b));
+  SAMPT_TRY(get_f32(c, c->fnet_prefix + name + ".weight_rsck", &w));
+  SAMPT_TRY(get_f32(c, c->fnet_prefix + name + ".bias", &b));
   return conv_nhwc_f32(c, st, in.p, w, b, out->p, in.n, in.h, in.w, in.c, out->c, R, R, stride, pad);
 }
 
@@ -94,23 +93,23 @@ static int fnet_chunk(Ctx* c, cudaStream_t st, const void* frames, int is_f32, i
   SAMPT_TRY(ws_get(c, &s.part, (size_t)n * nchunks * 256 * 2, "inorm partials"));
 
   Act x{bufA, n, H2, W2, 64};
-  g_im2col = nullptr;
-  if (fnet_uses_tc(c, g_prefix)) {
+  c->fnet_im2col = nullptr;
+  if (fnet_uses_tc(c, c->fnet_prefix)) {
     // largest im2col operand: max(layer1: H2*W2 x 2*576, conv2: Ho*Wo x 2*3776) halves per frame
     size_t a_elems = std::max((size_t)H2 * W2 * 2 * 576, (size_t)Ho * Wo * 2 * 3776) * n;
-    SAMPT_TRY(ws_get(c, &g_im2col, a_elems, "fnet im2col operand"));
+    SAMPT_TRY(ws_get(c, &c->fnet_im2col, a_elems, "fnet im2col operand"));
     const __half* w16; const float* b1;
-    SAMPT_TRY(get_f16(c, g_prefix + "fnet.conv1.w16", &w16));
-    SAMPT_TRY(get_f32(c, g_prefix + "fnet.conv1.bias", &b1));
-    SAMPT_TRY(im2col_conv1_split(c, st, frames, is_f32, g_im2col, n, H, W, 192));
+    SAMPT_TRY(get_f16(c, c->fnet_prefix + "fnet.conv1.w16", &w16));
+    SAMPT_TRY(get_f32(c, c->fnet_prefix + "fnet.conv1.bias", &b1));
+    SAMPT_TRY(im2col_conv1_split(c, st, frames, is_f32, c->fnet_im2col, n, H, W, 192));
     GemmSeg seg{3, {0, 192, 0}, {0, 0, 192}};
     GemmEpi ep{};
     ep.out32 = x.p; ep.bias = b1; ep.ldc = 64;
-    SAMPT_TRY(gemm_tc(c, st, g_im2col, 384, w16, 384, n * H2 * W2, 64, 192, seg, ep));
+    SAMPT_TRY(gemm_tc(c, st, c->fnet_im2col, 384, w16, 384, n * H2 * W2, 64, 192, seg, ep));
   } else {
     const float *w1, *b1;
-    SAMPT_TRY(get_f32(c, g_prefix + "fnet.conv1.weight_rsck", &w1));
-    SAMPT_TRY(get_f32(c, g_prefix + "fnet.conv1.bias", &b1));
+    SAMPT_TRY(get_f32(c, c->fnet_prefix + "fnet.conv1.weight_rsck", &w1));
+    SAMPT_TRY(get_f32(c, c->fnet_prefix + "fnet.conv1.bias", &b1));
     SAMPT_TRY(conv7x7s2(c, st, frames, is_f32, w1, b1, x.p, n, H, W));
   }
   SAMPT_TRY(inorm_stats(c, st, x.p, s.stats_a, s.part, n, H2 * W2, 64));
@@ -155,12 +154,12 @@ using namespace sampt;
 static int fnet_frames(Ctx* c, cudaStream_t st, const char* prefix, const void* frames, int is_f32, int T, int H, int W, int stride,
                        float* fmaps) {
   SAMPT_CHECK(stride == 4, "fnet: only stride 4 (configs/model/point_tracker/pips.yaml:3, cotracker_stride_4_wind_8) is built, got %d", stride);
-  g_prefix = prefix;
+  c->fnet_prefix = prefix;
   const int Ho = H / stride, Wo = W / stride;
   // chunk frames so the fp32 half-res activations fit the workspace (6 buffers of n*H2*W2*64 floats + concat)
   const int H2 = (H + 6 - 7) / 2 + 1, W2 = (W + 6 - 7) / 2 + 1;
   size_t per_frame = ((size_t)H2 * W2 * 64 * 5 + (size_t)Ho * Wo * 416) * sizeof(float) + (1 << 20);
-  if (fnet_uses_tc(c, g_prefix))
+  if (fnet_uses_tc(c, c->fnet_prefix))
     per_frame += std::max((size_t)H2 * W2 * 2 * 576, (size_t)Ho * Wo * 2 * 3776) * sizeof(__half);
   int chunk = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, (c->ws_bytes - (8u << 20)) / per_frame));
   SAMPT_CHECK(c->ws_bytes > per_frame + (8u << 20), "workspace too small for one frame of fnet (%zu needed)", per_frame + (8u << 20));
@@ -173,7 +172,7 @@ static int fnet_frames(Ctx* c, cudaStream_t st, const char* prefix, const void* 
     rc = fnet_chunk(c, st, reinterpret_cast<const char*>(frames) + (size_t)t0 * 3 * H * W * esz, is_f32, n, H, W, stride,
                     fmaps + (size_t)t0 * Ho * Wo * 128);
   }
-  g_prefix = "pips.";
+  c->fnet_prefix = "pips.";
   return rc;
 }
 

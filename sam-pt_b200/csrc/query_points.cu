@@ -36,33 +36,43 @@ kmed_dist_kernel(const float* __restrict__ pts, int n, float* __restrict__ D) {
   D[(size_t)i * n + j] = sqrtf(f);
 }
 
-// numpy's float32 pairwise sum over v(0..m-1); `at(j)` returns element j.
+// numpy's float32 pairwise sum over v(lo .. lo+m-1); `at(j)` returns element j.  The recursion depth is a template parameter
+// (m <= 128 * 2^DEPTH): compile-time bounded, so the compiler sizes the stack itself (true device recursion overflowed the
+// default 1 KB stack for n = 1800).
 template <typename F>
-__device__ float np_pairwise_sum(F at, int lo, int m) {
+__device__ __forceinline__ float np_pairwise_leaf(F at, int lo, int m) {
   if (m < 8) {
     float r = 0.f;
     for (int i = 0; i < m; ++i) r = __fadd_rn(r, at(lo + i));
     return r;
   }
-  if (m <= 128) {
-    float r[8];
+  float r[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) r[q] = at(lo + q);
-    int i = 8;
-    for (; i < m - (m % 8); i += 8) {
+  for (int q = 0; q < 8; ++q) r[q] = at(lo + q);
+  int i = 8;
+  for (; i < m - (m % 8); i += 8) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) r[q] = __fadd_rn(r[q], at(lo + i + q));
-    }
-    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-    for (; i < m; ++i) res = __fadd_rn(res, at(lo + i));
-    return res;
+    for (int q = 0; q < 8; ++q) r[q] = __fadd_rn(r[q], at(lo + i + q));
   }
-  int m2 = m / 2;
-  m2 -= m2 % 8;
-  const float a = np_pairwise_sum(at, lo, m2);
-  const float b = np_pairwise_sum(at, lo + m2, m - m2);
-  return __fadd_rn(a, b);
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < m; ++i) res = __fadd_rn(res, at(lo + i));
+  return res;
 }
+template <int DEPTH, typename F>
+__device__ float np_pairwise_sum_d(F at, int lo, int m) {
+  if constexpr (DEPTH == 0) {
+    return np_pairwise_leaf(at, lo, m);
+  } else {
+    if (m <= 128) return np_pairwise_leaf(at, lo, m);
+    int m2 = m / 2;
+    m2 -= m2 % 8;
+    const float a = np_pairwise_sum_d<DEPTH - 1>(at, lo, m2);
+    const float b = np_pairwise_sum_d<DEPTH - 1>(at, lo + m2, m - m2);
+    return __fadd_rn(a, b);
+  }
+}
+template <typename F>
+__device__ __forceinline__ float np_pairwise_sum(F at, int lo, int m) { return np_pairwise_sum_d<5>(at, lo, m); }   // m <= 4096
 
 __global__ void __launch_bounds__(128)
 kmed_rowsum_kernel(const float* __restrict__ D, int n, float* __restrict__ rowsum) {

@@ -167,11 +167,7 @@ template <int BM, int BN, int TM, int TN, int STAGES>
 static int launch_pipe(cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias, const float* residual,
                        int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
   constexpr size_t smem = (size_t)STAGES * (BM + BN) * 36 * sizeof(float);
-  static bool set = false;
-  if (!set) {
-    SAMPT_CUDA(cudaFuncSetAttribute(sgemm_pipe_kernel<BM, BN, TM, TN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set = true;
-  }
+  // the dynamic shared-memory limit of every instantiation is raised per device by sgemm_init() (called from sampt_ctx_create)
   dim3 grid(cdiv(N, BN), cdiv(M, BM));
   sgemm_pipe_kernel<BM, BN, TM, TN, STAGES><<<grid, 256, smem, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   return 0;

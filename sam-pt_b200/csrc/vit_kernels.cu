@@ -333,12 +333,10 @@ int attn_prep(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* 
   const int EXT = DK - HD;
   size_t smem = (size_t)TC * (HD + 8) * 2 * 2 + (size_t)TC * EXT * 2 + (size_t)(2 * S - 1) * (HD + 2) * sizeof(float);
   if (HD == 80) {
-    static bool set80 = false;
-    if (!set80) { SAMPT_CUDA(cudaFuncSetAttribute(attn_prep_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set80 = true; }
+    SAMPT_TRY(ensure_func_smem(c, "attn_prep_kernel<80>", attn_prep_kernel<80>, 160 * 1024));
     attn_prep_kernel<80><<<grid, 256, smem, st>>>(qkv, ldq, relh, relw, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC);
   } else {
-    static bool set64 = false;
-    if (!set64) { SAMPT_CUDA(cudaFuncSetAttribute(attn_prep_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set64 = true; }
+    SAMPT_TRY(ensure_func_smem(c, "attn_prep_kernel<64>", attn_prep_kernel<64>, 160 * 1024));
     attn_prep_kernel<64><<<grid, 256, smem, st>>>(qkv, ldq, relh, relw, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC);
   }
   c->launches++;

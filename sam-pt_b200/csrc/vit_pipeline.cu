@@ -22,7 +22,7 @@ __global__ void window_map_kernel(int* __restrict__ map, int B, int G, int ws, i
   map[r] = (y < G && x < G) ? (b * G * G + y * G + x) : -1;
 }
 
-// ---- EXPERIMENTAL (SAMPT_VIT_SKIP_PAD=1, off by default, not yet validated on hardware) -------------------------
+// ---- padding-window skip (ON by default, SAMPT_VIT_SKIP_PAD=0 disables; bit-identical, validated on hardware in round 2) -------
 // A non-square frame is zero-padded to 1024 x 1024 AFTER normalisation (upstream Sam.preprocess), so every token whose 14x14
 // window lies entirely in the padding is image-independent until the first GLOBAL attention block mixes all tokens: its
 // value after blocks 0..fg-1 is a constant of the model (weights + pos_embed).  For 480x854 input (576x1024 resized) that
@@ -75,7 +75,7 @@ __global__ void rows_scatter_bcast_kernel(const float* __restrict__ src, const i
   reinterpret_cast<float4*>(dst)[((size_t)b * GG + map[r]) * D4 + c] = reinterpret_cast<const float4*>(src)[(size_t)r * D4 + c];
 }
 static bool skip_pad_enabled() {
-  static const int on = [] { const char* e = std::getenv("SAMPT_VIT_SKIP_PAD"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+  static const int on = [] { const char* e = std::getenv("SAMPT_VIT_SKIP_PAD"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();   // validated on hardware in round 2: on unless =0
   return on != 0;
 }
 

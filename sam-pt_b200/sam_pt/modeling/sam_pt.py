@@ -393,6 +393,8 @@ class SamPt(nn.Module):
         want_interm = pred._uses_interm()
         main = torch.cuda.current_stream()
         nslot = max(1, int(self.decode_streams))
+        if not getattr(pred.model, "use_cuda_graphs", True) or not pred.model.has_decoder_slab():
+            nslot = 1   # the eager chain allocates from ONE shared workspace: concurrent streams would race on it
         if nslot > 1 and (self._dec_streams is None or len(self._dec_streams) != nslot):
             self._dec_streams = [torch.cuda.Stream(device=dev) for _ in range(nslot)]
         used = set()
@@ -426,8 +428,9 @@ class SamPt(nn.Module):
                             continue  # all points invisible -> mask stays -inf, score -inf (sam_pt.py:766-767,855)
                         c1024 = torch.as_tensor(pred.transform.apply_coords(coords, pred.original_size), dtype=torch.float, device=dev)
                         lab = torch.as_tensor(labels, dtype=torch.int, device=dev)
+                        pos_idx = np.nonzero(labels == 1)[0].tolist() if self.negative_points_per_mask > 0 else None
                         iou, _, _ = pred.predict_refine(c1024, lab, 1 if self.negative_points_per_mask > 0 else 0, n_ref, logits[m, i],
-                                                        slot=slot)
+                                                        slot=slot, positive_index=pos_idx)
                         # "Mask is empty if SAM's IoU score is too low" (sam_pt.py:833-835), without a host round trip
                         logits[m, i] = torch.where(iou[0] < thr, torch.full_like(logits[m, i], -float("inf")), logits[m, i])
                         scores_pf[i, m] = iou[0]

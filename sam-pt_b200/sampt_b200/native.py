@@ -75,6 +75,12 @@ class Context:
         self._dec_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         check(lib().sampt_ctx_set_decoder_workspace(self._h, ptr(self._dec_ws), c_size_t(nbytes)), "set_decoder_workspace")
 
+    def clear_decoder_workspace(self) -> None:
+        """No decoder slab: sampt_sam_predict_refine runs its eager chain out of the shared workspace (one stream only)."""
+        torch.cuda.synchronize(self.device)
+        self._dec_ws = None
+        check(lib().sampt_ctx_set_decoder_workspace(self._h, c_void_p(0), c_size_t(0)), "clear_decoder_workspace")
+
     def ensure_vit_workspace(self, nbytes: int) -> None:
         """Dedicated slab of the ViT encoder (lets it overlap with PIPS / decode on another stream)."""
         cur = getattr(self, "_vit_ws", None)

@@ -29,6 +29,10 @@ class Sam(nn.Module):
     def device(self):
         return self.pixel_mean.device
 
+    def has_decoder_slab(self) -> bool:
+        """True when the decode chain replays captured CUDA graphs out of per-slot buffers (several decode streams are safe)."""
+        return bool(self.use_cuda_graphs)
+
     # ------------------------------------------------------------------ decoder weights -> libsampt_b200
     def native_context(self) -> native.Context:
         ctx = self.image_encoder.native_context()
@@ -38,6 +42,8 @@ class Sam(nn.Module):
             self._register_decoder(ctx)
             if self.use_cuda_graphs:
                 ctx.set_decoder_workspace()  # also invalidates graphs captured with the previous weights
+            else:
+                ctx.clear_decoder_workspace()  # eager chain (single decode stream, see SamPt._apply_sam_to_frames)
             self._dec_registered = key
             ctx.claim("sam.decoder", self)
         return ctx

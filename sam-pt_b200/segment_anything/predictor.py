@@ -63,9 +63,18 @@ class SamPredictor:
     def encode_frames(self, frames_u8: torch.Tensor, want_interm: bool = False):
         """Batched set_image: (B,3,H,W) uint8 device frames -> features (B,256,64,64) [+ interm]."""
         resized = self.resize_frames_u8(frames_u8)
+        mean, std = self._pixel_stats()
+        return self.model.image_encoder.encode_resized_u8(resized, mean, std, want_interm=want_interm)
+
+    def _pixel_stats(self):
+        """pixel_mean / pixel_std as Python floats, read back ONCE per buffer version: a `.tolist()` per chunk is a blocking D2H
+        copy on the encoder stream, which would serialise the host behind the previous chunk's whole ViT."""
         m = self.model
-        return m.image_encoder.encode_resized_u8(resized, m.pixel_mean.flatten().tolist(), m.pixel_std.flatten().tolist(),
-                                                 want_interm=want_interm)
+        key = (m.pixel_mean.data_ptr(), m.pixel_mean._version, m.pixel_std.data_ptr(), m.pixel_std._version)
+        if getattr(self, "_pix_key", None) != key:
+            self._pix = (m.pixel_mean.flatten().tolist(), m.pixel_std.flatten().tolist())
+            self._pix_key = key
+        return self._pix
 
     def _uses_interm(self) -> bool:
         return False
@@ -166,7 +175,7 @@ class SamPredictor:
     # ------------------------------------------------------------------ fused SAM-PT refinement chain
     @torch.no_grad()
     def predict_refine(self, coords_1024: torch.Tensor, labels: torch.Tensor, n_positive_first: int, n_refine: int,
-                       logits_out: torch.Tensor, slot: int = 0):
+                       logits_out: torch.Tensor, slot: int = 0, positive_index=None):
         """SamPt.predict_mask (sam_pt/modeling/sam_pt.py:781-828) as ONE native call: 1 (or 2) initial predict_torch calls
         + `n_refine` box/mask refinement iterations with the break test on the device.  coords (K,2), labels (K,) int32 on
         the GPU; writes logits into `logits_out` (H,W) and returns (iou (1,), low_res (256,256), n_done (1,) int32)."""
@@ -181,9 +190,14 @@ class SamPredictor:
         K = coords_1024.shape[0]
         pos_c = pos_l = None
         if n_positive_first > 0:
-            sel = labels == 1
-            pos_c, pos_l = coords_1024[sel].contiguous(), labels[sel].contiguous()
-            n_positive_first = int(pos_c.shape[0])
+            if positive_index is not None:   # host-known indices of the positive points: no device-side boolean indexing / sync
+                idx = torch.as_tensor(positive_index, dtype=torch.long, device=dev)
+                pos_c, pos_l = coords_1024.index_select(0, idx).contiguous(), labels.index_select(0, idx).contiguous()
+                n_positive_first = len(positive_index)
+            else:
+                sel = labels == 1
+                pos_c, pos_l = coords_1024[sel].contiguous(), labels[sel].contiguous()
+                n_positive_first = int(pos_c.shape[0])
         ctx.ensure_workspace(256 << 20)
         native.check(native.lib().sampt_sam_predict_refine(
             ctx.handle, native.ptr(tok), c_int(g), native.ptr(coords_1024.contiguous()), native.ptr(labels.contiguous()), c_int(K),

@@ -29,9 +29,11 @@ class SamPredictor(_Base):
             interm = interm[0] if isinstance(interm, (list, tuple)) else interm
             it = interm.reshape(g * g, -1).contiguous().float()
             out = torch.empty((16 * g * g, 32), device=self.device, dtype=torch.float32)
-            ctx.ensure_workspace(256 << 20)
-            native.check(native.lib().sampt_sam_hq_features(ctx.handle, native.ptr(tok), native.ptr(it), c_int(g), native.ptr(out),
-                                                            native.stream_ptr()), "sam_hq_features")
+            # per-call scratch from the (stream-aware) torch allocator: the decode chains of different frames run concurrently
+            # on several streams, a shared workspace would race (round-1 advisor finding)
+            scratch = torch.empty((g * g * 1280,), device=self.device, dtype=torch.float32)
+            native.check(native.lib().sampt_sam_hq_features(ctx.handle, native.ptr(tok), native.ptr(it), c_int(g), native.ptr(scratch),
+                                                            native.ptr(out), native.stream_ptr()), "sam_hq_features")
             self._hq_feat, self._hq_src = out, self.features
         return self._hq_feat
 
@@ -52,9 +54,9 @@ class SamPredictor(_Base):
             native.check(native.lib().sampt_sam_set_hq_features(self.model.native_context().handle, None), "set_hq")
 
     @torch.no_grad()
-    def predict_refine(self, coords_1024, labels, n_positive_first, n_refine, logits_out, slot=0):
+    def predict_refine(self, coords_1024, labels, n_positive_first, n_refine, logits_out, slot=0, positive_index=None):
         self._select_hq(True)
         try:
-            return super().predict_refine(coords_1024, labels, n_positive_first, n_refine, logits_out, slot)
+            return super().predict_refine(coords_1024, labels, n_positive_first, n_refine, logits_out, slot, positive_index)
         finally:
             native.check(native.lib().sampt_sam_set_hq_features(self.model.native_context().handle, None), "set_hq")

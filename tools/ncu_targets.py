@@ -23,3 +23,4 @@ enc = SimpleNamespace(embed_dim=1280)
 model = SimpleNamespace(sam_predictor=SimpleNamespace(model=SimpleNamespace(image_encoder=enc)))
 print(bench.gemm_roofline(model, dev, SimpleNamespace(encoder_batch=10, precision=3)))
 print(bench.corr_roofline(dev))
+print(bench.attn_roofline(dev))
