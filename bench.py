@@ -41,6 +41,7 @@ CONFIGS = {
 TRACKER = {"C3": "cotracker", "C5": "cotracker"}   # every other config tracks with PIPS
 HQ_SAM = {"C5"}                                    # configs that use segment_anything_hq (MaskDecoderHQ + early ViT features)
 SAM_SEED, PIPS_SEED = 7202, 7201
+COT_COORD_SCALE = 0.001   # synth.condition_cotracker: contractive over the 12 chained windows of a 50-frame clip
 COT_VIS_BIAS = 0.6   # synth.condition_cotracker: ~90 % of the C3 / C5 query points visible (see its docstring)
 
 
@@ -131,10 +132,9 @@ def run_ours(args):
     cot_sd = None
     if tracker == "cotracker":
         from sam_pt.point_tracker.cotracker.cotracker import cotracker_shapes
-        cot_sd = synth.condition_cotracker(synth.make_state_dict(cotracker_shapes(), PIPS_SEED + 1), vis_bias=COT_VIS_BIAS)
-        args.no_cpu_baseline = True  # the CPU arm below times the PIPS path; C3 reports GPU numbers only
-        if world > 1:
-            args.mgpu_mode = "clip_per_gpu"  # the frame-sharded exchange is built for PIPS features
+        cot_sd = synth.condition_cotracker(synth.make_state_dict(cotracker_shapes(), PIPS_SEED + 1), vis_bias=COT_VIS_BIAS, coord_scale=COT_COORD_SCALE)
+        if not os.path.exists(os.path.join(ROOT, "tests", "golden", f"{args.config}_full_cpu.json")):
+            args.no_cpu_baseline = True   # no measured full-clip CPU run committed for this configuration
     model = factory.build_sam_pt(vit, sam_sd, ckpt, positive_points_per_mask=P, sam_iou_threshold=-1e9, device=dev, hq=hq,
                                  cotracker_state_dict=cot_sd)
     model.sam_predictor.model.image_encoder.precision = args.precision
@@ -244,8 +244,13 @@ def run_ours_frame_sharded(args, model, dev, rank, world, local):
     one NCCL all-gather of the PIPS feature maps (SamPt.forward_clips_sharded).  Weak scaling: clips/step == ranks."""
     import torch.distributed as dist
     from sampt_b200 import native, synth
+    from sampt_b200 import sharding
     T, H, W, vit, P = CONFIGS[args.config]
-    videos = [synth.make_video_dict(T, H, W, P, seed=72 + c) for c in range(world)]
+    tracker = TRACKER.get(args.config, "pips")
+    # clips per step: one per rank (weak scaling, BASELINE configs[3]) unless the configuration is ONE clip spread over the GPUs
+    # (BASELINE configs[4]: a single 100-frame 1080p clip on 8 GPUs -> strong scaling)
+    n_clips = args.clips_per_step if args.clips_per_step > 0 else (1 if args.config == "C5" else world)
+    videos = [synth.make_video_dict(T, H, W, P, seed=72 + c) for c in range(n_clips)]
     host = [dict(v, image=[f.pin_memory() for f in v["image"]]) for v in videos]
     resident = [dict(v, image=[f.to(dev) for f in v["image"]], query_points=v["query_points"].to(dev)) for v in videos]
     ctx = native.get_context(dev)
@@ -286,22 +291,22 @@ def run_ours_frame_sharded(args, model, dev, rank, world, local):
     ms, ms_e2e = t.tolist()
     roof = gemm_roofline(model, dev, args)
     if rank == 0:
-        frames_total = T * world * args.steps
-        own = len(range(rank, T, world))
+        frames_total = T * n_clips * args.steps
+        own = sum(len(sharding.owned_frames(T, rank, world, c)) for c in range(n_clips))
         line = {
             "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
             "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if n_clips == world else "strong", "vs_baseline": None,
             "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split (3 passes MLP, 2 passes qkv/proj)", 4: "f16 hi+lo split x3 (~fp32)"}[args.precision]
-                     + " ViT; f32 PIPS + decoder",
+                     + " ViT; f32 tracker + decoder",
             "data": "synthetic",
-            "config": {"workload": f"{world} x {args.config}: {T} frames {H}x{W}, SAM {vit} + PIPS, 1 mask x {P} points, 12 refinements; "
-                                   f"frames sharded round-robin over {world} GPUs, one NCCL all-gather of fp32 PIPS feature maps",
-                       "clips_per_step": world, "parallelism": f"frame-shard x{world} + all-gather",
+            "config": {"workload": f"{n_clips} x {args.config}: {T} frames {H}x{W}, {'HQ-' if args.config in HQ_SAM else ''}SAM {vit} + {tracker}, 1 mask x {P} points, 12 refinements; "
+                                   f"frame f of clip c on rank (f + c) mod {world}, one NCCL all-gather of the fp32 tracker feature maps",
+                       "clips_per_step": n_clips, "parallelism": f"frame-shard x{world} + all-gather",
                        "l2": "flushed between timed iterations (256 MiB write)", "vit_precision_passes": args.precision,
                        "encoder_batch": args.encoder_batch},
             "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": "frames/s",
-                    "h2d_bytes_per_step": int(world * own * 3 * H * W + world * P * 12), "d2h_bytes_per_step": int(d2h)},
+                    "h2d_bytes_per_step": int(own * 3 * H * W + n_clips * P * 12), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "cpu_baseline": None,
         }
         print(json.dumps(line))
@@ -607,6 +612,7 @@ def main():
     ap.add_argument("--breakdown", action="store_true")
     ap.add_argument("--kernel-table", default=None, help="write a per-kernel time table of one step (CUPTI) to this path")
     ap.add_argument("--mgpu-mode", default="frame_shard", choices=["frame_shard", "clip_per_gpu"])
+    ap.add_argument("--clips-per-step", type=int, default=0, help="N > 1: clips per step (default: one per rank; C5: a single clip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

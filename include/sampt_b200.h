@@ -68,6 +68,13 @@ int sampt_pips_pyramid(sampt_ctx* ctx, const float* fmaps, int T, int H4, int W4
 int sampt_pips_track(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3, int T, int H4,
                      int W4, const float* query_points, int N, int S, int stride, float thr0, int iters, int flip,
                      int max_windows, float* traj, float* vis, void* stream);
+/* Reference-compatible Pips.forward on ONE S-frame window (sam_pt/point_tracker/pips/pips.py:439-620, inference): the pyramid
+ * holds exactly S = 8 frames; xys [N,2] px; coords_init [S,N,2] px or NULL (zero-velocity init, :460-465); feat_init [N,128]
+ * or NULL (bilinear_sample2d of frame 0's features, :469-475) -> coords_out [iters,S,N,2] px (one entry per refinement
+ * iteration, :546), vis_e [S,N] raw visibility logits (:568), ffeat_out [N,128] the initial feature (`return_feat`, :617-618). */
+int sampt_pips_window(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3, int H4, int W4,
+                      const float* xys, const float* coords_init, const float* feat_init, int N, int S, int stride, int iters,
+                      float* coords_out, float* vis_e, float* ffeat_out, void* stream);
 /* CorrBlock.corr + CorrBlock.sample (pips.py:364-407) fused, for S window slots: ffeats (N,S,128), coords (N,S,2) in
  * level-0 feature pixels, pyramid levels (S,H_l,W_l,128) -> fcorr (N,S,196). */
 int sampt_pips_corr_lookup(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3, int S,
@@ -129,6 +136,12 @@ int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const
                              int H, int W, float* logits, float* iou, float* low_res, int* n_refine_done, int graph_slot,
                              void* stream);
 
+/* upstream ImageEncoderViT.forward(x): x = the already preprocessed float image (B,3,img_size,img_size) (Sam.preprocess output:
+ * normalised, zero-padded) -> features (B,out_chans,G,G) [+ first global block output].  Same pipeline as sampt_vit_encode with a
+ * plain float patch im2col; the padding-window skip is off (nothing is known about the padding of a float image). */
+int sampt_vit_encode_f32(sampt_ctx* ctx, const float* x, int B, int depth, int embed_dim, int num_heads, int window_size,
+                         const int* global_idx_host, int n_global, int img_size, int patch_size, int out_chans, int precision,
+                         float* features, float* interm, void* stream);
 /* Forget the image-independent ViT rows saved by the experimental SAMPT_VIT_SKIP_PAD=1 path (csrc/vit_pipeline.cu); to be
  * called whenever the image-encoder weights are re-registered.  A no-op when that path is off. */
 int sampt_vit_cache_clear(sampt_ctx* ctx);

@@ -54,7 +54,7 @@ def bounded_sample(H: int, W: int, P: int, tracker: str = "pips", hq: bool = Fal
         pips_ref.pips_forward(sd, q[0, :, 1:][None], None, None, 6, fmaps=fm[[0, 1, 1, 1, 1, 1, 1, 1]][None])
         t_trk = time.time() - t0
     else:
-        sd = synth.condition_cotracker(synth.make_state_dict(cotracker_ref.cotracker_state_dict_shapes(), PIPS_SEED + 1), vis_bias=0.6)
+        sd = synth.condition_cotracker(synth.make_state_dict(cotracker_ref.cotracker_state_dict_shapes(), PIPS_SEED + 1), vis_bias=0.6, coord_scale=0.001)
         ih, iw = 384, 512
         r = torch.nn.functional.interpolate(frames.float(), (ih, iw), mode="bilinear")
         x = 2 * (r / 255.0) - 1.0

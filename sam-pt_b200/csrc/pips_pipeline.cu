@@ -399,6 +399,113 @@ extern "C" int sampt_pips_track(sampt_ctx* ctx, const float* fmaps, const float*
   return rc_all;
 }
 
+namespace sampt {
+// helpers of sampt_pips_window (the reference-compatible Pips.forward on ONE S-frame window)
+__global__ void win_seed_kernel(const float* __restrict__ xys, float* __restrict__ traj, uint8_t* __restrict__ active, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  traj[(size_t)n * 2 + 0] = xys[(size_t)n * 2 + 0];     // frame 0 of the (S, N, 2) state = the query position
+  traj[(size_t)n * 2 + 1] = xys[(size_t)n * 2 + 1];
+  active[n] = 1;
+}
+// coords_init (S,N,2) px -> window state (N,S,2) feature-map px (pips.py:466: coords = coords_init.clone() / stride)
+__global__ void win_coords_in_kernel(const float* __restrict__ ci, float* __restrict__ coords, int N, int S, float inv_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * S) return;
+  const int n = i / S, s = i % S;
+  coords[(size_t)i * 2 + 0] = ci[((size_t)s * N + n) * 2 + 0] * inv_stride;
+  coords[(size_t)i * 2 + 1] = ci[((size_t)s * N + n) * 2 + 1] * inv_stride;
+}
+__global__ void win_feat_in_kernel(const float* __restrict__ fi, float* __restrict__ feat_init, float* __restrict__ ffeats, int N, int S) {
+  const int n = blockIdx.x, c = threadIdx.x;
+  const float f = fi[(size_t)n * 128 + c];
+  feat_init[(size_t)n * 128 + c] = f;
+  for (int s = 0; s < S; ++s) ffeats[((size_t)n * S + s) * 128 + c] = f;
+}
+// window state (N,S,2) feature-map px -> one slot of coord_predictions: (S,N,2) px (pips.py:546: coords * stride)
+__global__ void win_coords_out_kernel(const float* __restrict__ coords, float* __restrict__ out, int N, int S, float stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * S) return;
+  const int n = i / S, s = i % S;
+  out[((size_t)s * N + n) * 2 + 0] = coords[(size_t)i * 2 + 0] * stride;
+  out[((size_t)s * N + n) * 2 + 1] = coords[(size_t)i * 2 + 1] * stride;
+}
+// vis_e = Linear(128 -> 1)(ffeats)  (pips.py:568), raw logits (S,N); one warp per (n, s)
+__global__ void win_vis_kernel(const float* __restrict__ ffeats, const float* __restrict__ vw, const float* __restrict__ vb,
+                               float* __restrict__ vis_e, int N, int S) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= N * S) return;
+  const int n = wid / S, s = wid % S;
+  const float* ff = ffeats + (size_t)wid * 128;
+  float a = 0.f;
+  for (int k = lane; k < 128; k += 32) a = fmaf(vw[k], ff[k], a);
+  a = warp_sum(a);
+  if (lane == 0) vis_e[(size_t)s * N + n] = a + vb[0];
+}
+}  // namespace sampt
+
+// Reference-compatible Pips.forward on one S-frame window (sam_pt/point_tracker/pips/pips.py:439-620, inference):
+//   xys [N,2] px; coords_init [S,N,2] px or NULL (zero-velocity init from xys); feat_init [N,128] or NULL (bilinear sample of
+//   frame 0's feature map at xys / stride); `iters` refinement iterations ->
+//   coords_out [iters,S,N,2] px (coord_predictions, one entry per iteration), vis_e [S,N] raw visibility logits,
+//   ffeat_out [N,128] = the INITIAL feature (what `return_feat=True` returns, pips.py:617-618).
+// The pyramid (fmaps,l1,l2,l3) holds exactly S frames.
+extern "C" int sampt_pips_window(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3, int H4, int W4,
+                                 const float* xys, const float* coords_init, const float* feat_init, int N, int S, int stride, int iters,
+                                 float* coords_out, float* vis_e, float* ffeat_out, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  SAMPT_CHECK(S == 8, "sampt_pips_window: S must be 8, got %d", S);
+  SAMPT_CHECK(N > 0 && iters >= 0, "sampt_pips_window: empty input");
+  c->ws_reset();
+  MixerW m;
+  SAMPT_TRY(load_mixer(c, &m));
+  PipsWin w{};
+  w.N = N; w.S = S; w.stride = stride; w.T = S;
+  w.pyr[0] = fmaps; w.pyr[1] = l1; w.pyr[2] = l2; w.pyr[3] = l3;
+  w.H[0] = H4; w.W[0] = W4;
+  for (int l = 1; l < 4; ++l) { w.H[l] = w.H[l - 1] / 2; w.W[l] = w.W[l - 1] / 2; }
+  uint8_t* active_d; int* cur_d; int* wp_d; float *traj_d, *vis_d;
+  SAMPT_TRY(ws_get(c, &w.coords, (size_t)N * S * 2, "coords"));
+  SAMPT_TRY(ws_get(c, &w.ffeats, (size_t)N * S * 128, "ffeats"));
+  SAMPT_TRY(ws_get(c, &w.feat_init, (size_t)N * 128, "feat_init"));
+  SAMPT_TRY(ws_get(c, &active_d, (size_t)N, "active"));
+  SAMPT_TRY(ws_get(c, &cur_d, (size_t)N, "cur"));
+  SAMPT_TRY(ws_get(c, &wp_d, 16, "window params"));
+  SAMPT_TRY(ws_get(c, &traj_d, (size_t)S * N * 2, "traj"));
+  SAMPT_TRY(ws_get(c, &vis_d, (size_t)S * N, "vis"));
+  IterBufs b;
+  const int M = N * S;
+  SAMPT_TRY(ws_get(c, &b.xin, (size_t)M * 520, "xin"));
+  SAMPT_TRY(ws_get(c, &b.x, (size_t)M * 512, "x"));
+  SAMPT_TRY(ws_get(c, &b.xln, (size_t)M * 512, "xln"));
+  SAMPT_TRY(ws_get(c, &b.h, (size_t)M * 2048, "h"));
+  SAMPT_TRY(ws_get(c, &b.xm, (size_t)N * 512, "xm"));
+  SAMPT_TRY(ws_get(c, &b.delta, (size_t)N * S * 130, "delta"));
+  w.traj = traj_d; w.vis = vis_d; w.cur = cur_d; w.active = active_d; w.wp = wp_d;
+  SAMPT_CUDA(cudaMemsetAsync(b.xin, 0, (size_t)M * 520 * sizeof(float), st));
+  int* wp_h = reinterpret_cast<int*>(reinterpret_cast<char*>(c->pinned) + (64 << 10));
+  wp_h[0] = 0; wp_h[1] = 0;
+  for (int s = 0; s < S; ++s) wp_h[2 + s] = s;
+  SAMPT_CUDA(cudaMemcpyAsync(wp_d, wp_h, 10 * sizeof(int), cudaMemcpyHostToDevice, st));
+  win_seed_kernel<<<cdiv(N, 128), 128, 0, st>>>(xys, traj_d, active_d, N);
+  c->launches++;
+  w.sample_feat = feat_init ? 0 : 1;
+  if (feat_init) { win_feat_in_kernel<<<N, 128, 0, st>>>(feat_init, w.feat_init, w.ffeats, N, S); c->launches++; }
+  SAMPT_TRY(pips_window_init(c, st, w));   // zero-velocity coords from frame 0; ffeat sampled (or the given feat_init re-broadcast)
+  if (coords_init) { win_coords_in_kernel<<<cdiv(M, 256), 256, 0, st>>>(coords_init, w.coords, N, S, 1.0f / (float)stride); c->launches++; }
+  if (ffeat_out) SAMPT_CUDA(cudaMemcpyAsync(ffeat_out, w.feat_init, (size_t)N * 128 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int it = 0; it < iters; ++it) {
+    SAMPT_TRY(pips_iteration(c, st, w, m, b));
+    win_coords_out_kernel<<<cdiv(M, 256), 256, 0, st>>>(w.coords, coords_out + (size_t)it * S * N * 2, N, S, (float)stride);
+    c->launches++;
+  }
+  win_vis_kernel<<<cdiv((long long)M * 32, 256), 256, 0, st>>>(w.ffeats, m.vis_w, m.vis_b, vis_e, N, S);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  return 0;
+}
+
 // Unit-test entry: fused correlation lookup alone (the "first kernel").
 extern "C" int sampt_pips_corr_lookup(sampt_ctx* ctx, const float* fmaps, const float* l1, const float* l2, const float* l3,
                                       int S, int H4, int W4, const float* ffeats, const float* coords, int N, float* fcorr,

@@ -59,6 +59,29 @@ int pil_resize(Ctx* c, cudaStream_t st, const uint8_t* in, uint8_t* tmp, uint8_t
 //   A[(b*G + py)*G + px][c*P*P + iy*P + ix] = norm(img[b, c, py*P+iy, px*P+ix])   (0 beyond the resized image)
 // output fp16 hi (| lo at column split_off)
 // ---------------------------------------------------------------------------------------------------------------------
+// float variant: the image is ALREADY normalised and zero-padded (upstream ImageEncoderViT.forward(x) takes Sam.preprocess output)
+__global__ void im2col_f32_kernel(const float* __restrict__ img, __half* __restrict__ A, int G, int P, int ld, int split_off,
+                                  long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int K = 3 * P * P, S = G * P;
+  int k = (int)(i % K);
+  long long tok = i / K;
+  int px = (int)(tok % G), py = (int)((tok / G) % G), b = (int)(tok / ((long long)G * G));
+  int ch = k / (P * P), iy = (k / P) % P, ix = k % P;
+  const float v = img[(((size_t)b * 3 + ch) * S + py * P + iy) * S + px * P + ix];
+  __half h = __float2half_rn(v);
+  A[(size_t)tok * ld + k] = h;
+  if (split_off > 0) A[(size_t)tok * ld + split_off + k] = __float2half_rn(v - __half2float(h));
+}
+int im2col_f32(Ctx* c, cudaStream_t st, const float* img, __half* A, int B, int G, int P, int ld, int split_off) {
+  long long total = (long long)B * G * G * 3 * P * P;
+  im2col_f32_kernel<<<cdiv(total, 256), 256, 0, st>>>(img, A, G, P, ld, split_off, total);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, __half* __restrict__ A, int B, int Hr, int Wr, int G,
                                          int P, int ld, int split_off, float m0, float m1, float m2, float s0, float s1,
                                          float s2, long long total) {

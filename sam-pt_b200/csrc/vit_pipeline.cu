@@ -95,8 +95,12 @@ static GemmSeg make_seg(int precision, int K) {
 
 struct VitDims { int depth, D, nheads, window, G, P, C; };
 
-static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int Hr, int Wr, const VitDims& d, const int* global_idx,
-                       int n_global, int precision, const float* mean, const float* stdv, float* features, float* interm) {
+// img: uint8 frames resized so that the longest side == img_size (normalisation + zero padding fused into the patch im2col), OR
+// img_f32: the already preprocessed float image (B,3,img_size,img_size) of upstream ImageEncoderViT.forward (then Hr = Wr =
+// img_size: nothing is known about its padding, so the padding-window skip is off)
+static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float* img_f32, int B, int Hr, int Wr, const VitDims& d,
+                       const int* global_idx, int n_global, int precision, const float* mean, const float* stdv, float* features,
+                       float* interm) {
   const int D = d.D, G = d.G, GG = G * G, HD = D / d.nheads, ws = d.window;
   const int nW = (G + ws - 1) / ws, Lw = ws * ws;
   const int Mtok = B * GG, Mwin = B * nW * nW * Lw;
@@ -146,7 +150,7 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int H
   const int lwy = std::min(nW, (int)cdiv(cdiv(Hr, d.P), ws)), lwx = std::min(nW, (int)cdiv(cdiv(Wr, d.P), ws));
   const int rows_live = std::min(G, lwy * ws), cols_live = std::min(G, lwx * ws);
   const int nLW = lwy * lwx, nLT = rows_live * cols_live, n_const = GG - nLT;
-  const bool pad_candidate = skip_pad_enabled() && fg > 0 && fg < d.depth && n_const > 0;
+  const bool pad_candidate = skip_pad_enabled() && img_f32 == nullptr && fg > 0 && fg < d.depth && n_const > 0;
   int *wmap_c = nullptr, *tmap_c = nullptr, *cmap = nullptr;
   float* x_const = nullptr;   // [n_const, D] saved rows (library-owned, survives the call)
   bool compact = false;       // this call runs blocks < fg on the live rows only
@@ -180,7 +184,8 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, int B, int H
 
   // ---- patch embedding (Conv2d k=16 s=16 as a GEMM) + pos_embed
   {
-    SAMPT_TRY(preprocess_im2col(c, st, img, A, B, Hr, Wr, G, d.P, Kpe * asp, asp == 2 ? Kpe : 0, mean, stdv));
+    if (img_f32) SAMPT_TRY(im2col_f32(c, st, img_f32, A, B, G, d.P, Kpe * asp, asp == 2 ? Kpe : 0));
+    else SAMPT_TRY(preprocess_im2col(c, st, img, A, B, Hr, Wr, G, d.P, Kpe * asp, asp == 2 ? Kpe : 0, mean, stdv));
     const __half* w; const float *bias, *pos;
     SAMPT_TRY(get_f16(c, p + "patch_embed.w16", &w));
     SAMPT_TRY(get_f32(c, p + "patch_embed.proj.bias", &bias));
@@ -305,8 +310,22 @@ extern "C" int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B
   SAMPT_CHECK(Hr <= img_size && Wr <= img_size, "resized image (%dx%d) exceeds img_size %d", Hr, Wr, img_size);
   SAMPT_CHECK(embed_dim % 128 == 0 && embed_dim % num_heads == 0, "embed_dim must be a multiple of 128 and of num_heads");
   VitDims d{depth, embed_dim, num_heads, window_size, img_size / patch_size, patch_size, out_chans};
-  return vit_forward(c, reinterpret_cast<cudaStream_t>(stream), resized_u8, B, Hr, Wr, d, global_idx_host, n_global, precision,
+  return vit_forward(c, reinterpret_cast<cudaStream_t>(stream), resized_u8, nullptr, B, Hr, Wr, d, global_idx_host, n_global, precision,
                      pixel_mean_host, pixel_std_host, features, interm);
+}
+
+// upstream ImageEncoderViT.forward(x): x = preprocessed float image (B,3,img_size,img_size), i.e. Sam.preprocess output
+extern "C" int sampt_vit_encode_f32(sampt_ctx* ctx, const float* x, int B, int depth, int embed_dim, int num_heads, int window_size,
+                                    const int* global_idx_host, int n_global, int img_size, int patch_size, int out_chans,
+                                    int precision, float* features, float* interm, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  SAMPT_CHECK(precision >= 1 && precision <= 4, "sampt_vit_encode_f32: precision must be 1..4");
+  SAMPT_CHECK(img_size % patch_size == 0, "img_size must be a multiple of patch_size");
+  SAMPT_CHECK(embed_dim % 128 == 0 && embed_dim % num_heads == 0, "embed_dim must be a multiple of 128 and of num_heads");
+  VitDims d{depth, embed_dim, num_heads, window_size, img_size / patch_size, patch_size, out_chans};
+  const float zero[3] = {0.f, 0.f, 0.f}, one[3] = {1.f, 1.f, 1.f};
+  return vit_forward(c, reinterpret_cast<cudaStream_t>(stream), nullptr, x, B, img_size, img_size, d, global_idx_host, n_global,
+                     precision, zero, one, features, interm);
 }
 
 // drop the saved image-independent ViT rows (must be called whenever the image-encoder weights are re-registered)

@@ -358,16 +358,25 @@ class SamPt(nn.Module):
         """SAM on a subset of frames: images (n,3,H,W) uint8 on the device are the frames `frame_ids` of the clip whose
         full-clip trajectories (T,M,P,2) / visibilities (T,M,P) are given.  Returns logits (M,n,H,W), scores (n,M) on the
         device and `counted` (n,M) bool on the host (frames with at least one visible point)."""
+        return self._apply_sam_multi(images, [(0, f) for f in frame_ids], [(trajectories, visibilities)], pre=pre)[0]
+
+    @torch.no_grad()
+    def _apply_sam_multi(self, images, frame_specs, clips, pre=None):
+        """SAM over frames that may belong to SEVERAL clips (the frame-sharded multi-GPU path batches the owned frames of all
+        clips through the encoder together): images (n,3,H,W) uint8; frame_specs[i] = (clip index, frame id inside that clip);
+        clips[c] = (trajectories (T,M,P,2), visibilities (T,M,P)).  Per clip, in the order its frames appear in `images`:
+        (logits (M,n_c,H,W), scores (n_c,M) on the device, counted (n_c,M) bool on the host)."""
         n_sub, _, height, width = images.shape
-        n_frames, n_masks, points_per_mask, _ = trajectories.shape
-        assert visibilities.shape == (n_frames, n_masks, points_per_mask)
         dev = self.device
         pred = self.sam_predictor
-        # the only device->host copy before the results: a few KB of trajectories / visibility codes
-        traj_h = trajectories.detach().cpu()
-        vis_h = visibilities.detach().cpu()
+        # the only device->host copy before the results: a few KB of trajectories / visibility codes per clip
+        host = [(t.detach().cpu(), v.detach().cpu()) for t, v in clips]
+        for t, v in host:
+            assert v.shape == t.shape[:3]
 
-        def prepare_points(f, m):  # sam_pt.py:726-758
+        def prepare_points(c, f, m):  # sam_pt.py:726-758
+            traj_h, vis_h = host[c]
+            n_masks = traj_h.shape[1]
             pc = traj_h[f, m]
             labels = np.ones((len(pc)), dtype=int)
             if self.negative_points_per_mask > 0:
@@ -385,9 +394,14 @@ class SamPt(nn.Module):
                 labels = np.concatenate([labels, np.zeros((len(other)), dtype=int)], axis=0)
             return coords, labels
 
-        logits = torch.full((n_masks, n_sub, height, width), -float("inf"), device=dev, dtype=torch.float32)
-        scores_pf = torch.full((n_sub, n_masks), -float("inf"), device=dev, dtype=torch.float32)
-        counted = torch.zeros((n_sub, n_masks), dtype=torch.bool)
+        n_of = [sum(1 for c, _ in frame_specs if c == ci) for ci in range(len(clips))]
+        outs = []
+        for ci, (t, _) in enumerate(host):
+            M = t.shape[1]
+            outs.append([torch.full((M, n_of[ci], height, width), -float("inf"), device=dev, dtype=torch.float32),
+                         torch.full((n_of[ci], M), -float("inf"), device=dev, dtype=torch.float32),
+                         torch.zeros((n_of[ci], M), dtype=torch.bool)])
+        pos_in_clip = [0] * len(clips)
         n_ref = int(self.iterative_refinement_iterations) if self.iterative_refinement_iterations else 0
         B = max(1, int(self.encoder_batch))
         want_interm = pred._uses_interm()
@@ -399,11 +413,11 @@ class SamPt(nn.Module):
             self._dec_streams = [torch.cuda.Stream(device=dev) for _ in range(nslot)]
         used = set()
         thr = float(self.sam_iou_threshold)
-        for ci, f0 in enumerate(range(0, n_sub, B)):
+        for ci_chunk, f0 in enumerate(range(0, n_sub, B)):
             chunk = images[f0:f0 + B]
             ev = None
             if pre is not None:  # encoder output produced on the encoder stream (see _start_encoder)
-                enc, ev = pre[ci]
+                enc, ev = pre[ci_chunk]
             else:
                 enc = pred.encode_frames(chunk, want_interm=want_interm)
                 if nslot > 1:
@@ -412,7 +426,10 @@ class SamPt(nn.Module):
             feats, interm = enc if want_interm else (enc, None)
             for j in range(chunk.shape[0]):
                 i = f0 + j
-                f = frame_ids[i]
+                c, f = frame_specs[i]
+                k = pos_in_clip[c]
+                pos_in_clip[c] += 1
+                logits, scores_pf, counted = outs[c]
                 slot = i % nslot
                 stream = self._dec_streams[slot] if nslot > 1 else main
                 if nslot > 1 and slot not in used:
@@ -422,19 +439,19 @@ class SamPt(nn.Module):
                     if ev is not None:
                         stream.wait_event(ev)
                     pred.set_frames_features((height, width), (feats[j:j + 1], interm[j:j + 1]) if want_interm else feats[j:j + 1])
-                    for m in range(n_masks):
-                        coords, labels = prepare_points(f, m)
+                    for m in range(logits.shape[0]):
+                        coords, labels = prepare_points(c, f, m)
                         if len(coords) == 0:
                             continue  # all points invisible -> mask stays -inf, score -inf (sam_pt.py:766-767,855)
                         c1024 = torch.as_tensor(pred.transform.apply_coords(coords, pred.original_size), dtype=torch.float, device=dev)
                         lab = torch.as_tensor(labels, dtype=torch.int, device=dev)
                         pos_idx = np.nonzero(labels == 1)[0].tolist() if self.negative_points_per_mask > 0 else None
-                        iou, _, _ = pred.predict_refine(c1024, lab, 1 if self.negative_points_per_mask > 0 else 0, n_ref, logits[m, i],
+                        iou, _, _ = pred.predict_refine(c1024, lab, 1 if self.negative_points_per_mask > 0 else 0, n_ref, logits[m, k],
                                                         slot=slot, positive_index=pos_idx)
                         # "Mask is empty if SAM's IoU score is too low" (sam_pt.py:833-835), without a host round trip
-                        logits[m, i] = torch.where(iou[0] < thr, torch.full_like(logits[m, i], -float("inf")), logits[m, i])
-                        scores_pf[i, m] = iou[0]
-                        counted[i, m] = True
+                        logits[m, k] = torch.where(iou[0] < thr, torch.full_like(logits[m, k], -float("inf")), logits[m, k])
+                        scores_pf[k, m] = iou[0]
+                        counted[k, m] = True
             if nslot > 1:
                 for t in (enc if isinstance(enc, tuple) else (enc,)):
                     for sl in used:
@@ -442,18 +459,21 @@ class SamPt(nn.Module):
         if nslot > 1:
             for sl in used:
                 main.wait_stream(self._dec_streams[sl])
-        return logits, scores_pf, counted
+        return [tuple(o) for o in outs]
 
     # ------------------------------------------------------------------------------------------------ multi-GPU
     @torch.no_grad()
     def forward_clips_sharded(self, videos, gather_logits: bool = False):
         """Frame-sharded processing of `len(videos)` clips across the ranks of the default process group:
-        rank r owns frames {f : f mod G == r} of EVERY clip.
-          A. local : PIPS encoder (fnet) on the owned frames of every clip
-          B. NCCL  : ONE all-gather of the fp32 feature maps (13 MB/frame @480x854) -> every rank holds all features
-          C. local : linked tracker chain of clip c on rank c mod G (pyramid built locally after the gather)
+        frame f of clip c belongs to rank (f + c) mod G (sampt_b200/sharding.py: rotated round-robin, every rank owns the same
+        number of frames).
+          A. local : the tracker's encoder (PIPS fnet on uint8 frames; CoTracker: resize to interp_shape + fnet) on ALL owned
+                     frames of all clips in one pass; the SAM ViT on the same frames starts on its own stream, 10 frames per launch
+          B. NCCL  : ONE all-gather of the fp32 feature maps (13 MB/frame @480x854 for PIPS, 6.3 MB/frame @384x512 for
+                     CoTracker) -> every rank holds all features of every clip
+          C. local : tracker chain of clip c on rank c mod G (pyramid built locally after the gather)
           D. NCCL  : all-gather of the (T,N,3) trajectories/visibilities (a few KB)
-          E. local : SAM encode + prompt/mask decode on the owned frames of every clip
+          E. local : prompt + mask decode on the owned frames
         Returns, per clip, {"trajectories","visibilities","logits" (M, n_owned, H, W), "frame_ids", "scores_per_frame"}
         (logits stay sharded unless gather_logits)."""
         import torch.distributed as dist
@@ -461,60 +481,65 @@ class SamPt(nn.Module):
         world, rank = dist.get_world_size(), dist.get_rank()
         dev = self.device
         trk = self.point_tracker.to(dev)
-        if not hasattr(trk, "track_on_features"):
-            raise NotImplementedError("frame-sharded tracking is built for the PIPS tracker (BASELINE configs[3]); CoTracker clips "
-                                      "run one clip per GPU through SamPt.forward")
+        if not (hasattr(trk, "shard_features") and hasattr(trk, "track_on_features")):
+            raise NotImplementedError(f"{type(trk).__name__} has no frame-sharded path (needs shard_features / track_on_features)")
         C = len(videos)
-        T = len(videos[0]["image"])
-        own = sharding.owned_frames(T, rank, world)
-        # A. upload only the owned frames, encode them
-        own_frames, local_fm = [], []
-        for v in videos:
-            fr = torch.stack([v["image"][f].to(dev, non_blocking=True) for f in own], dim=0)
-            own_frames.append(fr)
-        pres = [self._start_encoder(fr) if self.overlap_streams else None for fr in own_frames]
-        for fr in own_frames:
-            local_fm.append(trk.model.fnet_frames(fr))
-        local = torch.stack(local_fm, dim=1)  # (n_own, C, H4, W4, 128): frame-major so one collective serves all clips
-        # B. the exchange step
-        full = sharding.allgather_frames(local, T)  # (T, C, H4, W4, 128)
+        Ts = [len(v["image"]) for v in videos]
+        own = [sharding.owned_frames(Ts[c], rank, world, c) for c in range(C)]
+        h, w = videos[0]["image"][0].shape[-2:]
+        # A. upload only the owned frames (async from pinned memory), one batch for every clip
+        specs = [(c, f) for c in range(C) for f in own[c]]
+        if len(specs) == 0:
+            all_own = torch.empty((0, 3, h, w), dtype=torch.uint8, device=dev)
+        else:
+            all_own = torch.stack([videos[c]["image"][f].to(dev, non_blocking=True) for c, f in specs], dim=0)
+        pre = self._start_encoder(all_own) if (self.overlap_streams and len(specs) > 0) else None
+        fm_all = trk.shard_features(all_own)                      # (n_own_total, H4, W4, 128)
+        locs, off = [], 0
+        for c in range(C):
+            locs.append(fm_all[off:off + len(own[c])])
+            off += len(own[c])
+        # B. the exchange step (one collective for all clips)
+        fulls = sharding.allgather_clips(locs, Ts)
         # C. chains: clip c on rank c % world
-        results = [None] * C
-        tv_local = []
-        shapes = []
+        tv_local, shapes = [], []
         for c, v in enumerate(videos):
             q = v["query_points"]
             M, P, _ = q.shape
             shapes.append((M, P))
             if c % world == rank:
-                pyr = trk.model.build_pyramid(full[:, c].contiguous())
-                traj, vis = trk.track_on_features(pyr, q.reshape(1, M * P, 3).to(dev))
+                traj, vis = trk.track_on_features(fulls[c], q.reshape(1, M * P, 3).to(dev), (h, w))
                 tv_local.append(torch.cat([traj[0], vis[0].float()[..., None]], dim=-1))  # (T, N, 3)
-        del full
+        del fulls
         # D. share the trajectories (tiny)
         N_max = max(m * p for m, p in shapes)
-        mine = torch.zeros((len(range(rank, C, world)), T, N_max, 3), device=dev)
-        for i, t in enumerate(tv_local):
-            mine[i, :, : t.shape[1]] = t
+        T_max = max(Ts)
         n_slots = (C + world - 1) // world
-        slab = torch.zeros((n_slots, T, N_max, 3), device=dev)
-        slab[: mine.shape[0]] = mine
-        gathered = torch.empty((world * n_slots, T, N_max, 3), device=dev)
+        slab = torch.zeros((n_slots, T_max, N_max, 3), device=dev)
+        for i, t in enumerate(tv_local):
+            slab[i, : t.shape[0], : t.shape[1]] = t
+        gathered = torch.empty((world * n_slots, T_max, N_max, 3), device=dev)
         dist.all_gather_into_tensor(gathered, slab)
         # E. SAM on the owned frames
-        h, w = own_frames[0].shape[-2:]
-        for c, v in enumerate(videos):
+        clips = []
+        for c in range(C):
             M, P = shapes[c]
-            tv = gathered[(c % world) * n_slots + c // world, :, : M * P]
-            traj = tv[..., :2].reshape(T, M, P, 2)
-            vis = tv[..., 2].reshape(T, M, P)
+            tv = gathered[(c % world) * n_slots + c // world, : Ts[c], : M * P]
+            traj = tv[..., :2].reshape(Ts[c], M, P, 2)
+            vis = tv[..., 2].reshape(Ts[c], M, P)
             out_code = float(PointVisibilityType.OUTSIDE_FRAME.value)
             oob = (traj[..., 0] / w < 0.01) | (traj[..., 1] / h < 0.01) | (traj[..., 0] / w > 0.99) | (traj[..., 1] / h > 0.99)
-            vis = torch.where(oob, torch.full_like(vis, out_code), vis)
-            logits, spf, _ = self._apply_sam_to_frames(own_frames[c], own, traj, vis, pre=pres[c])
-            res = {"trajectories": traj, "visibilities": vis, "logits": logits, "frame_ids": own, "scores_per_frame": spf}
-            if gather_logits:
-                res["logits"] = sharding.allgather_frames(logits.transpose(0, 1).contiguous(), T).transpose(0, 1)
-                res["frame_ids"] = list(range(T))
-            results[c] = res
+            clips.append((traj, torch.where(oob, torch.full_like(vis, out_code), vis)))
+        decoded = self._apply_sam_multi(all_own, specs, clips, pre=pre)
+        results = []
+        for c in range(C):
+            logits, spf, _ = decoded[c]
+            res = {"trajectories": clips[c][0], "visibilities": clips[c][1], "logits": logits, "frame_ids": own[c],
+                   "scores_per_frame": spf}
+            results.append(res)
+        if gather_logits:
+            for c in range(C):   # (clips may carry different numbers of masks: one collective per clip)
+                full = sharding.allgather_frames(results[c]["logits"].transpose(0, 1).contiguous(), Ts[c], clip=c)
+                results[c]["logits"] = full.transpose(0, 1)
+                results[c]["frame_ids"] = list(range(Ts[c]))
         return results

@@ -114,20 +114,30 @@ class CoTracker(nn.Module):
         return ctx
 
     # ------------------------------------------------------------------ per-frame work
-    def encode_frames(self, frames_f32: torch.Tensor) -> List[torch.Tensor]:
-        """(T,3,H,W) float32 0..255 -> channels-last pyramid [(T,H/4,W/4,128), /2, /4, /8]."""
+    def fnet_frames(self, frames_f32: torch.Tensor) -> torch.Tensor:
+        """(n,3,H,W) float32 0..255 -> (n,H/4,W/4,128) channels-last BasicEncoder features (once per frame)."""
         assert frames_f32.dtype == torch.float32 and frames_f32.is_cuda
         ctx = self.native_context()
         T, _, H, W = frames_f32.shape
         fm = torch.empty((T, H // 4, W // 4, LATENT), device=frames_f32.device, dtype=torch.float32)
-        native.check(native.lib().sampt_cotracker_fnet(ctx.handle, native.ptr(frames_f32.contiguous()), c_int(T), c_int(H), c_int(W),
-                                                       native.ptr(fm), native.stream_ptr()), "cotracker_fnet")
-        pyr = [fm] + [torch.empty((T, (H // 4) >> l, (W // 4) >> l, LATENT), device=fm.device, dtype=torch.float32)
-                      for l in range(1, 4)]
-        native.check(native.lib().sampt_pips_pyramid(ctx.handle, native.ptr(pyr[0]), c_int(T), c_int(H // 4), c_int(W // 4),
+        if T > 0:
+            native.check(native.lib().sampt_cotracker_fnet(ctx.handle, native.ptr(frames_f32.contiguous()), c_int(T), c_int(H), c_int(W),
+                                                           native.ptr(fm), native.stream_ptr()), "cotracker_fnet")
+        return fm
+
+    def build_pyramid(self, fm: torch.Tensor) -> List[torch.Tensor]:
+        """(T,H4,W4,128) -> [level0, /2, /4, /8] (upstream CorrBlock avg-pool pyramid)."""
+        ctx = self.native_context()
+        T, H4, W4, _ = fm.shape
+        pyr = [fm.contiguous()] + [torch.empty((T, H4 >> l, W4 >> l, LATENT), device=fm.device, dtype=torch.float32) for l in range(1, 4)]
+        native.check(native.lib().sampt_pips_pyramid(ctx.handle, native.ptr(pyr[0]), c_int(T), c_int(H4), c_int(W4),
                                                      native.ptr(pyr[1]), native.ptr(pyr[2]), native.ptr(pyr[3]),
                                                      native.stream_ptr()), "pyramid")
         return pyr
+
+    def encode_frames(self, frames_f32: torch.Tensor) -> List[torch.Tensor]:
+        """(T,3,H,W) float32 0..255 -> channels-last pyramid [(T,H/4,W/4,128), /2, /4, /8]."""
+        return self.build_pyramid(self.fnet_frames(frames_f32))
 
     # ------------------------------------------------------------------ upstream CoTracker.forward on pre-computed features
     def track(self, pyr: Sequence[torch.Tensor], queries: torch.Tensor, order: Sequence[int], iters: int = 6):

@@ -82,6 +82,24 @@ class CoTrackerPointTracker(PointTracker):
         if frames.dtype != torch.uint8:
             frames = frames.round().clamp(0, 255).to(torch.uint8)
         T, _, H, W = frames.shape
+        pyr = self.model.encode_frames(self.resize_clip(frames))
+        return self._track_pyramid(pyr, query_points, T, H, W)
+
+    # ---- frame-sharded multi-GPU path (SamPt.forward_clips_sharded): encoder on the owned frames, windows on gathered features
+    def shard_features(self, frames_u8):
+        """(n,3,H,W) uint8 frames this rank owns -> (n,ih/4,iw/4,128) fp32 features at the interp resolution (6.3 MB/frame @384x512)."""
+        frames_u8 = frames_u8.to(self.device)
+        if frames_u8.shape[0] == 0:
+            ih, iw = self.interp_shape
+            return torch.empty((0, ih // 4, iw // 4, 128), device=self.device, dtype=torch.float32)
+        return self.model.fnet_frames(self.resize_clip(frames_u8))
+
+    def track_on_features(self, fmaps, query_points, frame_hw):
+        """fmaps (T,ih/4,iw/4,128) of every frame in frame order (after the all-gather); frame_hw = input resolution (H, W)."""
+        return self._track_pyramid(self.model.build_pyramid(fmaps), query_points, fmaps.shape[0], int(frame_hw[0]), int(frame_hw[1]))
+
+    def _track_pyramid(self, pyr, query_points, T, H, W):
+        dev = self.device
         n_points = query_points.shape[1]
         ih, iw = self.interp_shape
         q = query_points[0].float().to(dev).clone()
@@ -93,7 +111,6 @@ class CoTrackerPointTracker(PointTracker):
                 g = get_points_on_a_grid(self.support_grid_size, self.interp_shape, device=dev)[0]
                 grids.append(torch.cat([torch.full_like(g[:, :1], float(i)), g], dim=1))
             q = torch.cat([q] + grids, dim=0)
-        pyr = self.model.encode_frames(self.resize_clip(frames))
         # CoTrackerForShortVideosWrapper (tracker.py:12-24): clips shorter than the window repeat their last frame
         pad = max(self.model.S - T, 0)
         order_fwd = list(range(T)) + [T - 1] * pad

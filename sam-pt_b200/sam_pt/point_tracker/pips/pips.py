@@ -145,23 +145,41 @@ class Pips(nn.Module):
     # ------------------------------------------------------------------ reference-compatible forward
     def forward(self, xys, rgbs, coords_init=None, feat_init=None, iters=3, trajs_g=None, vis_g=None, valids=None,
                 sw=None, return_feat=False, is_train=False):
-        """Reference `Pips.forward` (pips.py:439-620), inference subset: one S-frame window, zero-velocity init,
-        feature initialised from frame 0 (`feat_init=None`).  Returns (coord_predictions, coord_predictions2, vis_e,
-        losses=None).  The fused chain materialises only the final iteration, so every list entry is that estimate."""
-        if coords_init is not None or feat_init is not None or trajs_g is not None or is_train or self.training \
-                or return_feat:
-            raise NotImplementedError("B200 Pips.forward covers inference with coords_init=None, feat_init=None; the "
-                                      "feat_init hand-over between windows lives in sampt_pips_track")
-        B, N, _ = xys.shape
+        """Reference `Pips.forward` (pips.py:439-620), inference: one S-frame window.
+        xys (1,N,2) px, rgbs (1,S,3,H,W) 0..255, coords_init (1,S,N,2) px or None (zero-velocity init, :460-465), feat_init
+        (1,N,128) or None (bilinear sample of frame 0, :469-475) -> (coord_predictions: `iters` tensors (1,S,N,2), one per
+        refinement iteration (:546); coord_predictions2: the same list bracketed by two copies of the initial and two of the final
+        estimate (:479-480,571-572); vis_e (1,S,N) raw logits (:568); [ffeat (1,N,128) if return_feat (:617-618);] losses=None).
+        One native call (`sampt_pips_window`)."""
+        if trajs_g is not None or is_train or self.training or (sw is not None and getattr(sw, "save_this", False)):
+            raise NotImplementedError("B200 Pips.forward covers inference (no losses / training / summary writer)")
+        B, N, D = xys.shape
+        assert D == 2
         if B != 1:
             raise NotImplementedError("Batch size > 1 is not supported for PIPS yet")
         assert rgbs.shape[1] == self.S
-        frames = rgbs[0]
+        dev = self.norm.weight.device
+        frames = rgbs[0].to(dev)
         if frames.dtype != torch.uint8:
             frames = frames.round().clamp(0, 255).to(torch.uint8)
         pyr = self.encode_frames(frames)
-        q = torch.cat([torch.zeros((N, 1), device=xys.device), xys[0].float()], dim=1)
-        traj, vis = self.track(pyr, q, thr0=0.9, iters=iters, max_windows=1)
-        coords = traj[None]
-        vis_e = torch.logit(vis.clamp(1e-7, 1 - 1e-7))[None]
-        return [coords for _ in range(iters)], [coords for _ in range(iters + 4)], vis_e, None
+        ctx = self.native_context()
+        S = self.S
+        H4, W4 = pyr[0].shape[1:3]
+        q = xys[0].detach().float().to(dev).contiguous()
+        ci = coords_init[0].detach().float().to(dev).contiguous() if coords_init is not None else None
+        fi = feat_init[0].detach().float().to(dev).contiguous() if feat_init is not None else None
+        coords_out = torch.empty((max(iters, 1), S, N, 2), device=dev, dtype=torch.float32)
+        vis_e = torch.empty((S, N), device=dev, dtype=torch.float32)
+        ffeat = torch.empty((N, LATENT), device=dev, dtype=torch.float32)
+        native.check(native.lib().sampt_pips_window(
+            ctx.handle, native.ptr(pyr[0]), native.ptr(pyr[1]), native.ptr(pyr[2]), native.ptr(pyr[3]), c_int(H4), c_int(W4),
+            native.ptr(q), native.ptr(ci), native.ptr(fi), c_int(N), c_int(S), c_int(self.stride), c_int(iters), native.ptr(coords_out),
+            native.ptr(vis_e), native.ptr(ffeat), native.stream_ptr()), "pips_window")
+        init = (ci if ci is not None else q[None].repeat(S, 1, 1))[None]
+        preds = [coords_out[i][None] for i in range(iters)]
+        last = preds[-1] if iters > 0 else init
+        preds2 = [init, init] + preds + [last, last]
+        if return_feat:
+            return preds, preds2, vis_e[None], ffeat[None], None
+        return preds, preds2, vis_e[None], None

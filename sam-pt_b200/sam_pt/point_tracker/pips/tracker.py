@@ -36,11 +36,19 @@ class PipsPointTracker(PointTracker):
         if frames.dtype != torch.uint8:
             frames = frames.round().clamp(0, 255).to(torch.uint8)
         pyr = self.model.encode_frames(frames)
-        return self.track_on_features(pyr, query_points)
+        return self._track_pyramid(pyr, query_points)
 
-    def track_on_features(self, pyr, query_points):
-        """The linked bidirectional chain on pre-computed feature pyramids (used directly by the frame-sharded multi-GPU
-        path, where the per-frame features arrive through an all-gather)."""
+    # ---- frame-sharded multi-GPU path (SamPt.forward_clips_sharded): encoder on the owned frames, chain on gathered features
+    def shard_features(self, frames_u8):
+        """(n,3,H,W) uint8 frames this rank owns -> (n,H/4,W/4,128) fp32 BasicEncoder features (the all-gather payload)."""
+        return self.model.fnet_frames(frames_u8.to(self.device))
+
+    def track_on_features(self, fmaps, query_points, frame_hw=None):
+        """fmaps (T,H/4,W/4,128): every frame's features in frame order (after the all-gather); the pyramid is built locally."""
+        return self._track_pyramid(self.model.build_pyramid(fmaps), query_points)
+
+    def _track_pyramid(self, pyr, query_points):
+        """The linked bidirectional chain on pre-computed feature pyramids."""
         dev = self.device
         q = query_points[0].float().to(dev)
         T = pyr[0].shape[0]

@@ -129,8 +129,20 @@ class ImageEncoderViT(nn.Module):
         return (feats, interm) if want_interm else feats
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """Upstream signature: x = preprocessed float image (B,3,img,img).  The fused path consumes uint8 pixels, so the
-        float interface is only accepted when it is an exactly de-normalisable uint8 image (SamPredictor uses
-        `encode_resized_u8`)."""
-        raise NotImplementedError("call encode_resized_u8 (used by SamPredictor.set_image); the float-input forward of the "
-                                  "reference is replaced by a fused uint8 -> normalise -> patch-embed path")
+        """Upstream signature: x = preprocessed float image (B,3,img_size,img_size) (`Sam.preprocess` output) -> (B,out_chans,g,g).
+        (SamPredictor uses `encode_resized_u8`, which fuses the normalisation and zero padding into the patch im2col.)"""
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.img_size or x.shape[3] != self.img_size:
+            raise ValueError(f"expected a (B,3,{self.img_size},{self.img_size}) image, got {tuple(x.shape)}")
+        ctx = self.native_context()
+        dev = self.pos_embed.device
+        x = x.to(dev, torch.float32).contiguous()
+        B = x.shape[0]
+        g = self.img_size // self.patch_size
+        ctx.ensure_vit_workspace(self.workspace_bytes(B))
+        feats = torch.empty((B, self.out_chans, g, g), device=dev, dtype=torch.float32)
+        gidx = (c_int * max(1, len(self.global_attn_indexes)))(*self.global_attn_indexes)
+        native.check(native.lib().sampt_vit_encode_f32(
+            ctx.handle, native.ptr(x), c_int(B), c_int(self.depth), c_int(self.embed_dim), c_int(self.num_heads), c_int(self.window_size),
+            gidx, c_int(len(self.global_attn_indexes)), c_int(self.img_size), c_int(self.patch_size), c_int(self.out_chans),
+            c_int(self.precision), native.ptr(feats), native.ptr(None), native.stream_ptr()), "vit_encode_f32")
+        return feats

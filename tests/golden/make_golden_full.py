@@ -41,6 +41,7 @@ from sampt_b200 import synth  # noqa: E402
 from oracle import cotracker_ref, cpu_sample, pips_ref, sam_ref, sampt_ref  # noqa: E402
 
 SAM_SEED, PIPS_SEED = 7202, 7201          # = bench.py / tests
+COT_COORD_SCALE = 0.001   # synth.condition_cotracker: contractive over the 12 chained windows of a 50-frame clip
 COT_VIS_BIAS = 0.6                        # synth.condition_cotracker: ~90 % of the C3 / C5 query points visible
 CONFIGS = {
     # name: T, H, W, P, tracker, hq, clip seed, frames kept (slice of the clip the oracle runs on)
@@ -99,7 +100,7 @@ def main():
         tracker = lambda im, q: (traj_ref, vis_ref)          # noqa: E731  (the reference's own output feeds SAM)
         pips_sd_arg = None
     else:
-        cot_sd = synth.condition_cotracker(synth.make_state_dict(cotracker_ref.cotracker_state_dict_shapes(), PIPS_SEED + 1), vis_bias=COT_VIS_BIAS)
+        cot_sd = synth.condition_cotracker(synth.make_state_dict(cotracker_ref.cotracker_state_dict_shapes(), PIPS_SEED + 1), vis_bias=COT_VIS_BIAS, coord_scale=COT_COORD_SCALE)
         box = {}
 
         def tracker(im, q):

@@ -100,12 +100,12 @@ def test_tracker_wrapper_vs_oracle(T):
     d = (traj.cpu() - traj_ref).abs().max().item()
     agree = (vis.cpu() == vis_ref).float().mean().item()
     print(f"cotracker wrapper T={T}: max |traj - oracle| = {d:.2e} px, visibility agreement {agree:.3f}, visible {vis_ref.float().mean():.2f}")
-    assert d < 3e-3
+    assert d < 1e-3          # north-star bar (measured ~3e-5 px)
     assert agree >= 0.97
 
 
 def test_tensor_core_encoder_end_to_end():
-    """default configuration (encoder convolutions on tcgen05 with the 3-pass split): trajectories within 0.02 px of the oracle."""
+    """default configuration (encoder convolutions on tcgen05 with the 3-pass split): trajectories within 1e-3 px of the oracle."""
     from oracle import cotracker_ref as R
     sd = _weights()
     T, H, W = 12, 96, 128
@@ -117,7 +117,7 @@ def test_tensor_core_encoder_end_to_end():
     traj, _ = trk(frames[None].cuda(), q.cuda())
     d = (traj.cpu() - traj_ref).abs().max().item()
     print(f"cotracker wrapper (TC encoder): max |traj - oracle| = {d:.2e} px")
-    assert d < 0.02
+    assert d < 1e-3
 
 
 @pytest.mark.parametrize("hq", [False, True])
@@ -152,11 +152,14 @@ def test_sampt_with_cotracker_end_to_end(tmp_path, hq):
     for m in range(2):
         for f in range(10):
             a, b = out["logits"][m][f].cpu(), ref["logits"][m][f]
-            iou, flipped, area = _iou(a, b), int(((a > 0) != (b > 0)).sum()), int((b > 0).sum())
+            diff = (a > 0) != (b > 0)
+            iou, flipped, area = _iou(a, b), int(diff.sum()), int((b > 0).sum())
             print_rows.append((iou, flipped, area))
-            # north-star bar: IoU >= 0.999.  The random-weight HQ branch yields ~180 px masks, where ONE undecided pixel
-            # (|logit| ~ 1e-2 after 12 box/mask refinements) already costs 0.0056 IoU: there the bar is "at most 2 such pixels"
-            assert iou >= 0.999 or (area < 2000 and flipped <= 2), (m, f, iou, flipped, area)
+            # north-star bar: IoU >= 0.999.  Logit-margin criterion for the tiny (~180 px) masks of the random-weight HQ branch,
+            # where one pixel is 0.0056 IoU: a disagreeing pixel is tolerated only if the ORACLE itself is undecided there
+            # (|logit| < 1e-2 of a field whose typical magnitude is O(1)), and at most 2 of them per mask
+            margin_ok = flipped <= 2 and (flipped == 0 or float(b[diff].abs().max()) < 1e-2)
+            assert iou >= 0.999 or margin_ok, (m, f, iou, flipped, area)
     print(f"SamPt + CoTracker (hq={hq}): max |dcoord| = {terr:.2e} px, min mask IoU = {min(r[0] for r in print_rows):.5f}, "
           f"flipped pixels = {sum(r[1] for r in print_rows)}, mask areas {min(r[2] for r in print_rows)}..{max(r[2] for r in print_rows)} px")
 

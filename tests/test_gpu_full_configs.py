@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SAM_SEED, PIPS_SEED = 7202, 7201
+COT_COORD_SCALE = 0.001   # synth.condition_cotracker: contractive over the 12 chained windows of a 50-frame clip
 COT_VIS_BIAS = 0.6   # synth.condition_cotracker: ~90 % of the C3 / C5 query points visible (see its docstring)
 
 
@@ -43,7 +44,7 @@ def _run_and_compare(config, tmp_path, traj_tol=1e-3, iou_bar=0.999):
         model = factory.build_sam_pt("vit_h", sam_sd, ckpt, positive_points_per_mask=P, sam_iou_threshold=-1e9, hq=hq)
     else:
         from sam_pt.point_tracker.cotracker.cotracker import cotracker_shapes
-        cot_sd = synth.condition_cotracker(synth.make_state_dict(cotracker_shapes(), PIPS_SEED + 1), vis_bias=COT_VIS_BIAS)
+        cot_sd = synth.condition_cotracker(synth.make_state_dict(cotracker_shapes(), PIPS_SEED + 1), vis_bias=COT_VIS_BIAS, coord_scale=COT_COORD_SCALE)
         model = factory.build_sam_pt("vit_h", sam_sd, None, positive_points_per_mask=P, sam_iou_threshold=-1e9, hq=hq,
                                      cotracker_state_dict=cot_sd)
     out = model(video)

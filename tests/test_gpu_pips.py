@@ -107,11 +107,41 @@ def test_single_window_matches_reference_golden(gold, model):
     c = g["cfg"]
     clip = synth.make_clip(c["T"], c["H"], c["W"], seed=c["seed"])
     xys = synth.make_query_points(clip, c["P"], seed=c["seed"])[:, :, 1:]
-    preds, _, vis_e, _ = model(xys.cuda(), clip["frames"][None].cuda(), iters=6)
-    got = preds[-1][0].cpu()
-    ref = g["coords_per_iter"][-1]
-    assert (got[1:] - ref[1:]).abs().max() < 1e-3
-    assert torch.allclose(torch.sigmoid(vis_e[0, 1:].cpu()), torch.sigmoid(g["vis_e"][1:]), atol=1e-4)
+    preds, preds2, vis_e, ffeat, losses = model(xys.cuda(), clip["frames"][None].cuda(), iters=6, return_feat=True)
+    # the full reference contract (pips.py:617-620): one coordinate estimate PER ITERATION, raw visibility logits, the initial
+    # feature, losses=None; coord_predictions2 brackets the list with two copies of the initial and of the final estimate
+    assert losses is None and len(preds) == 6 and len(preds2) == 10
+    for it in range(6):
+        assert (preds[it][0].cpu() - g["coords_per_iter"][it]).abs().max() < 1e-3, it
+    assert torch.equal(preds2[0], preds2[1]) and torch.equal(preds2[-1], preds[-1]) and torch.equal(preds2[2], preds[0])
+    assert (preds2[0][0, :, :, :].cpu() - xys[0][None]).abs().max() == 0          # zero-velocity initialisation
+    assert (vis_e[0].cpu() - g["vis_e"]).abs().max() < 1e-3 * max(1.0, g["vis_e"].abs().max().item())
+    assert (ffeat[0].cpu() - g["ffeat"]).abs().max() < 1e-4 * max(1.0, g["ffeat"].abs().max().item())
+    # feat_init hand-over (the tracker's update pass, pips/tracker.py:93-101): golden run with xys + 3 px and the stored feature
+    preds_f, _, vis_f, _ = model(xys.cuda() + 3.0, clip["frames"][None].cuda(), feat_init=g["ffeat"][None].cuda(), iters=6)
+    assert (preds_f[-1][0].cpu() - g["coords_feat_init"]).abs().max() < 1e-3
+    assert (vis_f[0].cpu() - g["vis_e_feat_init"]).abs().max() < 1e-3 * max(1.0, g["vis_e_feat_init"].abs().max().item())
+    # coords_init: starting every slot at the query position IS the zero-velocity default
+    ci = xys[0][None].repeat(8, 1, 1)[None]
+    preds_c, _, _, _ = model(xys.cuda(), clip["frames"][None].cuda(), coords_init=ci.cuda(), iters=6)
+    assert torch.equal(preds_c[-1], preds[-1])
+
+
+def test_evaluate_batch_contract(sd, tmp_path):
+    """PointTracker.evaluate_batch / unpack_results (reference sam_pt/point_tracker/tracker.py:47-118): forward + shape check +
+    results detached, cloned and moved to the CPU under the reference's keys."""
+    trk = _tracker(sd, tmp_path)
+    clip = synth.make_clip(9, 64, 96, seed=3)
+    q = synth.make_query_points(clip, 3, seed=3)
+    traj, vis = trk(clip["frames"][None].cuda(), q.cuda())
+    out = trk.evaluate_batch(clip["frames"][None].cuda(), q.cuda(), trajectories_gt=traj, visibilities_gt=vis)
+    assert set(out) == {"trajectories_pred", "visibilities_pred", "query_points", "trajectories_gt", "visibilities_gt"}
+    assert all(not v.is_cuda for v in out.values())
+    assert out["trajectories_pred"].shape == (1, 9, 3, 2) and out["visibilities_pred"].shape == (1, 9, 3)
+    assert torch.equal(out["trajectories_pred"], traj.cpu()) and torch.equal(out["visibilities_pred"], vis.cpu())
+    rows = trk.unpack_results(out, batch_idx=7)
+    assert len(rows) == 3 and rows[1]["idx"] == "7_0_1" and rows[1]["trajectory_pred"].shape == (9, 2)
+    assert torch.equal(rows[2]["trajectory_gt"], traj[0, :, 2].cpu())
 
 
 def _tracker(sd, tmp_path):

@@ -27,6 +27,12 @@ def _worker(rank, world, port, T, ret):
     mine = full[sharding.owned_frames(T, rank, world)]
     got = sharding.allgather_frames(mine, T)
     ok = torch.equal(got, full) and torch.equal(sharding.scatter_rows_by_frame(got, rank, world), mine)
+    # several clips of different lengths in ONE collective, ownership rotated per clip: owner(f, c) = (f + c) mod G
+    Ts = [T, T + 3, max(T - 1, 1)]
+    fulls = [torch.arange(t * 4, dtype=torch.float32).reshape(t, 4) + 1000 * c for c, t in enumerate(Ts)]
+    locs = [fulls[c][sharding.owned_frames(t, rank, world, c)] for c, t in enumerate(Ts)]
+    gots = sharding.allgather_clips(locs, Ts)
+    ok = ok and all(torch.equal(g, f) for g, f in zip(gots, fulls))
     t = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     # max-over-ranks timing reduction used by bench.py
@@ -75,10 +81,15 @@ def test_owned_frames_partition_every_world_size():
     from sampt_b200 import sharding
     for world in (1, 2, 4, 8):
         for T in (2, 50, 100):
-            owned = [sharding.owned_frames(T, r, world) for r in range(world)]
-            assert sorted(f for o in owned for f in o) == list(range(T))
-            n = sharding.padded_count(T, world)
-            assert all(len(o) <= n for o in owned) and max(len(o) for o in owned) == n
-            # the gather's reorder index is a permutation onto the un-padded rows
-            idx = [(f % world) * n + f // world for f in range(T)]
-            assert len(set(idx)) == T and all(i < world * n for i in idx)
+            for clip in range(world):
+                owned = [sharding.owned_frames(T, r, world, clip) for r in range(world)]
+                assert sorted(f for o in owned for f in o) == list(range(T))
+                assert all(sharding.owner(f, clip, world) == r for r, o in enumerate(owned) for f in o)
+                n = sharding.padded_count(T, world)
+                assert all(len(o) <= n for o in owned) and max(len(o) for o in owned) == n
+                # the gather's reorder index is a permutation onto the un-padded rows
+                idx = sharding._gather_index(T, world, clip, n)
+                assert len(set(idx)) == T and all(i < world * n for i in idx)
+            # G clips of T frames: the rotation gives every rank exactly T frames (round 1: 56 vs 48 at T=50, G=8)
+            per_rank = [sum(len(sharding.owned_frames(T, r, world, c)) for c in range(world)) for r in range(world)]
+            assert per_rank == [T] * world, (world, T, per_rank)
