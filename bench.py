@@ -41,6 +41,9 @@ CONFIGS = {
 TRACKER = {"C3": "cotracker", "C5": "cotracker"}   # every other config tracks with PIPS
 HQ_SAM = {"C5"}                                    # configs that use segment_anything_hq (MaskDecoderHQ + early ViT features)
 SAM_SEED, PIPS_SEED = 7202, 7201
+PRECISION_NAMES = {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)",
+                   3: "f16 hi+lo split (3 passes MLP, 2 passes qkv/proj)", 4: "f16 hi+lo split x3 (~fp32)",
+                   5: "f16 hi+lo split (3 passes MLP + proj, 2 passes qkv)"}
 COT_COORD_SCALE = 0.001   # synth.condition_cotracker: contractive over the 12 chained windows of a 50-frame clip
 COT_VIS_BIAS = 0.6   # synth.condition_cotracker: ~90 % of the C3 / C5 query points visible (see its docstring)
 
@@ -215,8 +218,7 @@ def run_ours(args):
             "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
             "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split (3 passes MLP, 2 passes qkv/proj)", 4: "f16 hi+lo split x3 (~fp32)"}[args.precision]
-                     + " ViT; f32 PIPS + decoder",
+            "dtype": PRECISION_NAMES[args.precision] + " ViT; f32 PIPS + decoder",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {T} frames {H}x{W}, {'HQ-' if hq else ''}SAM {vit} + {'CoTracker (S=8, stride 4, interp 384x512)' if tracker == 'cotracker' else 'PIPS (S=8, stride 4)'}, 1 mask x {P} points, "
                                    f"12 refinement iterations, random-init conditioned weights",
@@ -297,8 +299,7 @@ def run_ours_frame_sharded(args, model, dev, rank, world, local):
             "metric": "frames/sec, SAM-PT hot path (PIPS track + SAM ViT encode + prompt/mask decode w/ 12 refinements)",
             "value": frames_total / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if n_clips == world else "strong", "vs_baseline": None,
-            "dtype": {1: "f16 (fp32 accumulate)", 2: "f16 x (f16 hi+lo weights), 2 passes (fp32 accumulate)", 3: "f16 hi+lo split (3 passes MLP, 2 passes qkv/proj)", 4: "f16 hi+lo split x3 (~fp32)"}[args.precision]
-                     + " ViT; f32 tracker + decoder",
+            "dtype": PRECISION_NAMES[args.precision] + " ViT; f32 tracker + decoder",
             "data": "synthetic",
             "config": {"workload": f"{n_clips} x {args.config}: {T} frames {H}x{W}, {'HQ-' if args.config in HQ_SAM else ''}SAM {vit} + {tracker}, 1 mask x {P} points, 12 refinements; "
                                    f"frame f of clip c on rank (f + c) mod {world}, one NCCL all-gather of the fp32 tracker feature maps",

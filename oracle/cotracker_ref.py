@@ -217,7 +217,7 @@ def get_points_on_a_grid(grid_size: int, interp_shape: Tuple[int, int]):
 
 @torch.no_grad()
 def cotracker_point_tracker_forward(sd: SD, rgbs_u8, query_points, interp_shape=(384, 512), visibility_threshold=0.7,
-                                    support_grid_size=2, support_grid_every_n_frames=12):
+                                    support_grid_size=2, support_grid_every_n_frames=12, raw: Optional[dict] = None):
     """CoTrackerPointTracker.forward (cotracker/tracker.py:72-152) incl. the short-clip wrapper and the backward pass."""
     query_points = query_points.float()
     rgbs = rgbs_u8.float()
@@ -250,6 +250,8 @@ def cotracker_point_tracker_forward(sd: SD, rgbs_u8, query_points, interp_shape=
     traj[mask] = traj_f[mask]
     vis[mask[:, :, :, 0]] = vis_f[mask[:, :, :, 0]]
     traj = traj[:, :, :n_points].clone()
+    if raw is not None:   # the sigmoid values the threshold is applied to (tests: how close to the decision boundary?)
+        raw["vis_sigmoid"] = vis[:, :, :n_points].clone()
     vis = vis[:, :, :n_points].clone() > visibility_threshold
     traj[:, :, :, 0] *= W / float(interp_shape[1])
     traj[:, :, :, 1] *= H / float(interp_shape[0])

@@ -140,7 +140,13 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint32_t idesc_qk = make_idesc_f16(128, p.NT, 0);
       const uint32_t idesc_pv = make_idesc_f16(128, p.HD, 0);
       const int nk16 = p.NT / 16;
-      auto issue_qk_now = [&](int t, int g) {          // all inputs ready (polled by the scheduler loop below)
+      auto issue_qk = [&](int t, int g) {
+        const int il = t / p.ntiles, j = t % p.ntiles;
+        if (g == 0) {
+          if (j == 0) mbar_wait(q_full, il & 1);
+          mbar_wait(k_full, t & 1);
+        }
+        if (t >= 1) mbar_wait(s_free + g, (t - 1) & 1);           // WG g has read O_{t-1} out of its TMEM region
         tc_fence_after();
         const uint32_t tS = tmem_base + (uint32_t)(g * 256);
         for (int kb = 0; kb < p.DKB; ++kb) {
@@ -150,8 +156,13 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int k = 0; k < 4; ++k) umma_f16(tS, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc_qk, (kb | k) != 0);
         }
         umma_commit(s_full + g);
+        if (g == 1) {
+          umma_commit(k_empty);
+          if (j == p.ntiles - 1) umma_commit(q_empty);
+        }
       };
-      auto issue_pv_now = [&](int t, int g) {
+      auto issue_pv = [&](int t, int g) {
+        mbar_wait(p_full + g, t & 1);
         tc_fence_after();
         const uint32_t tP = tmem_base + (uint32_t)(g * 256);
         const uint32_t tO = tP + (uint32_t)(((p.NT / 2 + 31) / 32) * 32);
@@ -161,46 +172,19 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         umma_commit(o_full + g);
       };
-      // Event-driven issue: poll (non-blocking) which of the four next operations -- QK^T / P.V of either warpgroup -- has its
-      // inputs ready and issue that one.  (A fixed order PV0 QK0' PV1 QK1' made warpgroup 1 wait for warpgroup 0's O read-out
-      // before its own P.V could even be issued: 22 % of all warp samples sat in that wait, profiles/r02_attention.md.)
-      int qk_t[2] = {0, 0}, pv_t[2] = {0, 0};
-      int v_ready = -1;          // highest tile whose V^T is known to have landed
-      while (pv_t[0] < T || pv_t[1] < T) {
-        bool progressed = false;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          // P.V of warpgroup g
-          const int tp = pv_t[g];
-          if (tp < T && tp < qk_t[g]) {
-            if (v_ready < tp && mbar_try_wait(v_full, tp & 1)) v_ready = tp;
-            if (v_ready >= tp && mbar_try_wait(p_full + g, tp & 1)) {
-              issue_pv_now(tp, g);
-              pv_t[g] = tp + 1;
-              if (pv_t[0] > tp && pv_t[1] > tp) umma_commit(v_empty);   // both P.V of tile tp issued: V^T buffer free when they finish
-              progressed = true;
-            }
-          }
-          // QK^T of warpgroup g (tile tq): needs K'_tq (hence both QK^T of tile tq-1 issued), Q' of its item, and the warpgroup's
-          // TMEM region (O_{tq-1} read out)
-          const int tq = qk_t[g];
-          if (tq < T && tq <= qk_t[g ^ 1] && (tq == 0 || pv_t[g] >= tq)) {
-            const int il = tq / p.ntiles, j = tq % p.ntiles;
-            bool ok = mbar_try_wait(k_full, tq & 1);
-            if (ok && j == 0) ok = mbar_try_wait(q_full, il & 1);
-            if (ok && tq >= 1) ok = mbar_try_wait(s_free + g, (tq - 1) & 1);
-            if (ok) {
-              issue_qk_now(tq, g);
-              qk_t[g] = tq + 1;
-              if (qk_t[0] > tq && qk_t[1] > tq) {                        // both QK^T of tile tq issued
-                umma_commit(k_empty);
-                if (j == p.ntiles - 1) umma_commit(q_empty);
-              }
-              progressed = true;
-            }
-          }
-        }
-        (void)progressed;
+      // Issue order  QK0 QK1 | PV0 QK0' PV1 QK1' | ...  (blocking waits).  An event-driven variant that polled the four candidate
+      // operations with try_wait was measured SLOWER (windowed 0.169 vs 0.150 ms, global 2.20 vs 1.84 ms per launch): a poll sweep
+      // costs several try_wait latencies, a blocking wait wakes at once.  The softmax chain (IPC 0.4 per sub-partition at 2 warps),
+      // not the issue order, is what bounds the kernel (profiles/r02_attention.md).
+      issue_qk(0, 0);
+      issue_qk(0, 1);
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(v_full, t & 1);
+        issue_pv(t, 0);
+        if (t + 1 < T) issue_qk(t + 1, 0);
+        issue_pv(t, 1);
+        umma_commit(v_empty);
+        if (t + 1 < T) issue_qk(t + 1, 1);
       }
     }
   } else {

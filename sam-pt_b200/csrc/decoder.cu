@@ -5,8 +5,11 @@
 // Every kernel takes a `skip` flag pointer: once the refinement loop's break condition (mask area < 2 px, sam_pt.py:812)
 // has fired on the device, the remaining iterations' kernels return immediately, so the whole 13-call chain of a frame is
 // enqueued without a single host synchronisation (the reference does ~6 syncs per iteration).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_api.cuh"
 #include "../../include/sampt_b200.h"
 
 namespace sampt {
@@ -648,7 +651,11 @@ __global__ void init_ctl_kernel(int* bbox, int* skip, int* n_done) {
 // ====================================================================================================================
 // host orchestration
 // ====================================================================================================================
-struct AttnW { const float *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob; int internal; };
+struct AttnW {
+  const float *qw, *qb, *kw, *kb, *vw, *vb, *ow, *ob; int internal;
+  // image-side projections on tcgen05: weights as fp16 hi|lo [N, 2K] (null: that projection is token-side only)
+  const __half *qw16 = nullptr, *kw16 = nullptr, *vw16 = nullptr, *ow16 = nullptr;
+};
 struct LayerW {
   AttnW self_attn, t2i, i2t;
   const float *n1w, *n1b, *n2w, *n2b, *n3w, *n3b, *n4w, *n4b;
@@ -659,6 +666,8 @@ struct DecW {
   LayerW layer[2];
   AttnW final_attn; const float *nfw, *nfb, *pek_final;
   const float *up0_w /*[256 tok-in][4*64]^T as [4*64][256]*/, *up0_b4 /*[256] bias tiled over the 4 sub-pixels*/;
+  const __half* up0_w16 = nullptr;  // the same matrix as fp16 hi|lo [256, 512] for the tcgen05 path
+  bool tc = false;                  // image-side GEMMs (4096-row operands) on the tcgen05 split-precision GEMM
   const float *up_lnw, *up_lnb, *up3_w, *up3_b;
   Mlp3Job hyper[4], iou;
   DenseW dense;
@@ -681,6 +690,11 @@ static int load_attn(Ctx* c, const std::string& p, AttnW* a, int internal) {
   SAMPT_TRY(get_f32(c, p + "out_proj.weight", &a->ow)); SAMPT_TRY(get_f32(c, p + "out_proj.bias", &a->ob));
   return 0;
 }
+static bool decoder_tc_enabled() {
+  static const int on = [] { const char* e = std::getenv("SAMPT_DECODER_TC"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+static int load_w16(Ctx* c, const std::string& name, const __half** out) { return get_f16(c, name, out); }
 static int load_mlp3(Ctx* c, const std::string& p, Mlp3Job* j, int n_out) {
   SAMPT_TRY(get_f32(c, p + "layers.0.weight", &j->w0)); SAMPT_TRY(get_f32(c, p + "layers.0.bias", &j->b0));
   SAMPT_TRY(get_f32(c, p + "layers.1.weight", &j->w1)); SAMPT_TRY(get_f32(c, p + "layers.1.bias", &j->b1));
@@ -705,6 +719,19 @@ static int load_dec(Ctx* c, DecW* w) {
     SAMPT_TRY(get_f32(c, lp + "pek_t2i", &L.pek_t2i)); SAMPT_TRY(get_f32(c, lp + "peq_i2t", &L.peq_i2t));
   }
   SAMPT_TRY(load_attn(c, tr + "final_attn_token_to_image.", &w->final_attn, 128));
+  w->tc = decoder_tc_enabled() && c->find(md + "output_upscaling.0.w16") != nullptr;
+  if (w->tc) {
+    for (int i = 0; i < 2; ++i) {
+      const std::string lp = tr + "layers." + std::to_string(i) + ".";
+      SAMPT_TRY(load_w16(c, lp + "cross_attn_token_to_image.k_proj.w16", &w->layer[i].t2i.kw16));
+      SAMPT_TRY(load_w16(c, lp + "cross_attn_token_to_image.v_proj.w16", &w->layer[i].t2i.vw16));
+      SAMPT_TRY(load_w16(c, lp + "cross_attn_image_to_token.q_proj.w16", &w->layer[i].i2t.qw16));
+      SAMPT_TRY(load_w16(c, lp + "cross_attn_image_to_token.out_proj.w16", &w->layer[i].i2t.ow16));
+    }
+    SAMPT_TRY(load_w16(c, tr + "final_attn_token_to_image.k_proj.w16", &w->final_attn.kw16));
+    SAMPT_TRY(load_w16(c, tr + "final_attn_token_to_image.v_proj.w16", &w->final_attn.vw16));
+    SAMPT_TRY(load_w16(c, md + "output_upscaling.0.w16", &w->up0_w16));
+  }
   SAMPT_TRY(get_f32(c, tr + "norm_final_attn.weight", &w->nfw)); SAMPT_TRY(get_f32(c, tr + "norm_final_attn.bias", &w->nfb));
   SAMPT_TRY(get_f32(c, tr + "pek_final", &w->pek_final));
   SAMPT_TRY(get_f32(c, md + "output_upscaling.0.weight_gemm", &w->up0_w));
@@ -749,6 +776,7 @@ static int load_dec(Ctx* c, DecW* w) {
 struct DecBufs {
   float *tokens, *queries, *qpe, *tq, *tk, *tv, *ta, *tmp, *mlp_h;   // token side  (T rows)
   float *src, *keys, *ik, *iv, *iq, *ia;                            // image side  (4096 rows)
+  __half *keys16 = nullptr, *ia16 = nullptr;                         // fp16 hi|lo copies of keys [GG,512] / ia [GG,256] (tcgen05 path)
   float *u1, *hyper, *iou4, *part;
   float *u_sam, *mf1, *mf2;  // HQ only
   int T;
@@ -761,13 +789,57 @@ static int sg(Ctx* c, cudaStream_t st, const float* X, int ldx, const float* W, 
   return sgemm_nt_skip(c, st, X, ldx, W, K, b, resid, ldr, Y, ldy, M, N, K, act, skip);
 }
 
+// x [rows, K] fp32 -> out [rows, 2K] fp16: hi = fp16(x) | lo = fp16(x - hi)   (A operand of the split-precision tcgen05 GEMM)
+__global__ void __launch_bounds__(256)
+split_f32_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n4 /* rows*K/4 */, int K, const int* skip) {
+  SKIP_RETURN(skip);
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const long long e = i * 4;
+  const long long r = e / K;
+  const int cidx = (int)(e % K);
+  const float4 v = *reinterpret_cast<const float4*>(x + e);
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+  __half* o = out + r * 2 * K + cidx;
+  *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  *reinterpret_cast<uint2*>(o + K) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+static int split_rows(Ctx* c, cudaStream_t st, const float* x, __half* out, int rows, int K, const int* skip) {
+  const long long n4 = (long long)rows * K / 4;
+  split_f32_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, out, n4, K, skip);
+  c->launches++;
+  SAMPT_LAUNCH_CHECK();
+  return 0;
+}
+// Y = X W^T + b (+ resid), X given as fp16 hi|lo [M, 2K], W as fp16 hi|lo [N, 2K]: three tcgen05 passes A_hi.B_hi + A_lo.B_hi +
+// A_hi.B_lo into one fp32 TMEM accumulator (products exact to ~2^-22: the decoder stays at fp32-level accuracy).  The residual is
+// indexed like Y (same leading dimension).
+static int tcg(Ctx* c, cudaStream_t st, const __half* X16, const __half* W16, const float* b, const float* resid, float* Y, int ldy,
+               int M, int N, int K, const int* skip) {
+  GemmSeg seg{};
+  seg.nseg = 3;
+  seg.a_off[0] = 0; seg.b_off[0] = 0;
+  seg.a_off[1] = K; seg.b_off[1] = 0;
+  seg.a_off[2] = 0; seg.b_off[2] = K;
+  GemmEpi ep{};
+  ep.out32 = Y; ep.ldc = ldy; ep.bias = b; ep.resid = resid; ep.skip = skip;
+  return gemm_tc(c, st, X16, 2 * K, W16, 2 * K, M, N, K, seg, ep);
+}
+
 // tokens -> image attention: queries attend over the 4096 image tokens.  q_in already includes the query PE.
 static int attn_tok_to_img(Ctx* c, cudaStream_t st, const AttnW& a, const float* q_in, const float* keys, const float* pek,
                            DecBufs& b, float* out /*[T,256]*/, const float* resid, int GG, const int* skip) {
   const int T = b.T;
   SAMPT_TRY(sg(c, st, q_in, 256, a.qw, a.qb, nullptr, 0, b.tq, 128, T, 128, 256, 0, skip));
-  SAMPT_TRY(sg(c, st, keys, 256, a.kw, a.kb, pek, 128, b.ik, 128, GG, 128, 256, 0, skip));   // (keys + key_pe) Wk^T
-  SAMPT_TRY(sg(c, st, keys, 256, a.vw, a.vb, nullptr, 0, b.iv, 128, GG, 128, 256, 0, skip));
+  if (a.kw16 != nullptr) {   // tcgen05: b.keys16 holds the hi|lo split of `keys` (kept in sync by the caller)
+    SAMPT_TRY(tcg(c, st, b.keys16, a.kw16, a.kb, pek, b.ik, 128, GG, 128, 256, skip));           // (keys + key_pe) Wk^T
+    SAMPT_TRY(tcg(c, st, b.keys16, a.vw16, a.vb, nullptr, b.iv, 128, GG, 128, 256, skip));
+  } else {
+    SAMPT_TRY(sg(c, st, keys, 256, a.kw, a.kb, pek, 128, b.ik, 128, GG, 128, 256, 0, skip));   // (keys + key_pe) Wk^T
+    SAMPT_TRY(sg(c, st, keys, 256, a.vw, a.vb, nullptr, 0, b.iv, 128, GG, 128, 256, 0, skip));
+  }
   {
     constexpr int KPS = 256;
     const int nsplit = (GG + KPS - 1) / KPS;
@@ -813,7 +885,8 @@ static int two_way_layer(Ctx* c, cudaStream_t st, const LayerW& L, int idx, DecB
   // (4) cross attention image -> tokens
   add_kernel<<<cdiv(T * 64, 256), 256, 0, st>>>(b.queries, b.tokens, b.qpe, (long long)T * 64, skip);
   LAUNCH_OK();
-  SAMPT_TRY(sg(c, st, b.keys, 256, L.i2t.qw, L.i2t.qb, L.peq_i2t, 128, b.iq, 128, GG, 128, 256, 0, skip));  // (keys+pe) Wq^T
+  if (L.i2t.qw16 != nullptr) SAMPT_TRY(tcg(c, st, b.keys16, L.i2t.qw16, L.i2t.qb, L.peq_i2t, b.iq, 128, GG, 128, 256, skip));
+  else SAMPT_TRY(sg(c, st, b.keys, 256, L.i2t.qw, L.i2t.qb, L.peq_i2t, 128, b.iq, 128, GG, 128, 256, 0, skip));  // (keys+pe) Wq^T
   SAMPT_TRY(sg(c, st, b.qpe, 256, L.i2t.kw, L.i2t.kb, nullptr, 0, b.tk, 128, T, 128, 256, 0, skip));
   SAMPT_TRY(sg(c, st, b.queries, 256, L.i2t.vw, L.i2t.vb, nullptr, 0, b.tv, 128, T, 128, 256, 0, skip));
   {
@@ -823,9 +896,15 @@ static int two_way_layer(Ctx* c, cudaStream_t st, const LayerW& L, int idx, DecB
     attn_kv_small_kernel<16><<<cdiv((long long)GG * 8, 256), 256, smem, st>>>(b.iq, b.tk, b.tv, b.ia, GG, T, 8, TCH, skip);
     LAUNCH_OK();
   }
-  SAMPT_TRY(sg(c, st, b.ia, 128, L.i2t.ow, L.i2t.ob, b.keys, 256, b.src, 256, GG, 256, 128, 0, skip));   // keys + attn_out
+  if (L.i2t.ow16 != nullptr) {
+    SAMPT_TRY(split_rows(c, st, b.ia, b.ia16, GG, 128, skip));
+    SAMPT_TRY(tcg(c, st, b.ia16, L.i2t.ow16, L.i2t.ob, b.keys, b.src, 256, GG, 256, 128, skip));          // keys + attn_out
+  } else {
+    SAMPT_TRY(sg(c, st, b.ia, 128, L.i2t.ow, L.i2t.ob, b.keys, 256, b.src, 256, GG, 256, 128, 0, skip));   // keys + attn_out
+  }
   ln256_kernel<<<cdiv(GG, 8), 256, 0, st>>>(b.src, nullptr, L.n4w, L.n4b, b.keys, GG, 1e-5f, skip);
   LAUNCH_OK();
+  if (L.i2t.ow16 != nullptr) SAMPT_TRY(split_rows(c, st, b.keys, b.keys16, GG, 256, skip));   // keys changed: refresh the hi|lo copy
   return 0;
 }
 
@@ -855,6 +934,7 @@ static int decode_once(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, const Decod
   dense_src_kernel<<<cdiv(GG, 8), 256, 0, st>>>(d.feat_tok, d.mask_in, w.dense, b.keys, G, d.skip);
   LAUNCH_OK();
   SAMPT_CUDA(cudaMemcpyAsync(b.queries, b.tokens, (size_t)T * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (w.tc) SAMPT_TRY(split_rows(c, st, b.keys, b.keys16, GG, 256, d.skip));
   for (int i = 0; i < 2; ++i) SAMPT_TRY(two_way_layer(c, st, w.layer[i], i, b, GG, d.skip));
   // final token -> image attention
   add_kernel<<<cdiv(T * 64, 256), 256, 0, st>>>(b.queries, b.tokens, b.qpe, (long long)T * 64, d.skip);
@@ -884,7 +964,8 @@ static int decode_once(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, const Decod
   mlp3_kernel<<<njobs, 256, 0, st>>>(jobs, d.skip);
   LAUNCH_OK();
   // upscaling: ConvT(256->64) as GEMM [GG,256] x [256(4 sub-pixels x 64), 256]^T, then fused LN+GELU+ConvT+GELU+hyper dot
-  SAMPT_TRY(sg(c, st, b.keys, 256, w.up0_w, w.up0_b4, nullptr, 0, b.u1, 256, GG, 256, 256, 0, d.skip));
+  if (w.tc) SAMPT_TRY(tcg(c, st, b.keys16, w.up0_w16, w.up0_b4, nullptr, b.u1, 256, GG, 256, 256, d.skip));
+  else SAMPT_TRY(sg(c, st, b.keys, 256, w.up0_w, w.up0_b4, nullptr, 0, b.u1, 256, GG, 256, 256, 0, d.skip));
   upscale_mask_kernel<<<cdiv(16 * GG, 256), 256, 0, st>>>(b.u1, w.up_lnw, w.up_lnb, w.up3_w, w.up3_b, b.hyper, d.n_masks, d.low_res,
                                                          G, hq ? b.u_sam : nullptr, d.skip);
   LAUNCH_OK();
@@ -922,6 +1003,8 @@ static int alloc_dec_bufs(Ctx* c, DecBufs* b, int Tmax, int GG) {
   SAMPT_TRY(ws_get(c, &b->iv, (size_t)GG * 128, "dec iv"));
   SAMPT_TRY(ws_get(c, &b->iq, (size_t)GG * 128, "dec iq"));
   SAMPT_TRY(ws_get(c, &b->ia, (size_t)GG * 128, "dec ia"));
+  SAMPT_TRY(ws_get(c, &b->keys16, (size_t)GG * 512, "dec keys16"));
+  SAMPT_TRY(ws_get(c, &b->ia16, (size_t)GG * 256, "dec ia16"));
   SAMPT_TRY(ws_get(c, &b->u1, (size_t)GG * 256, "dec u1"));
   SAMPT_TRY(ws_get(c, &b->hyper, (size_t)8 * 32, "dec hyper"));
   SAMPT_TRY(ws_get(c, &b->u_sam, (size_t)16 * GG * 32, "dec u_sam"));
@@ -1063,6 +1146,7 @@ static int carve_slot(Ctx* c, DecW& w, const RefineShape& s, bool hq, int Kcap, 
   DG(b.mlp_h, (size_t)Tmax * 2048, "mlp_h");
   DG(b.src, (size_t)GG * 256, "src"); DG(b.keys, (size_t)GG * 256, "keys"); DG(b.ik, (size_t)GG * 128, "ik"); DG(b.iv, (size_t)GG * 128, "iv");
   DG(b.iq, (size_t)GG * 128, "iq"); DG(b.ia, (size_t)GG * 128, "ia"); DG(b.u1, (size_t)GG * 256, "u1"); DG(b.hyper, 256, "hyper");
+  DG(b.keys16, (size_t)GG * 512, "keys16"); DG(b.ia16, (size_t)GG * 256, "ia16");
   if (hq) { DG(b.u_sam, (size_t)16 * GG * 32, "u_sam"); DG(b.mf1, (size_t)16 * GG * 64, "mf1"); DG(b.mf2, (size_t)16 * GG * 32, "mf2"); }
   else { b.u_sam = b.mf1 = b.mf2 = nullptr; }
   DG(b.iou4, 8, "iou4"); DG(b.part, (size_t)Tmax * 8 * ((GG + 255) / 256) * 18, "attn partials");

@@ -85,6 +85,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, GemmSeg seg,
                 GemmEpi ep) {
+  if (ep.skip != nullptr && *ep.skip != 0) return;   // uniform over the grid (both CTAs of every pair): nothing allocated yet
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES);

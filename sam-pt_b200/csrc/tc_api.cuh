@@ -16,6 +16,7 @@ struct GemmEpi {
   int split_off = 0;             // >0: also write lo = fp16(v - hi) at column offset split_off (out16 only)
   int is_bf16 = 0;
   int resid_mod = 0;             // >0: residual row = dest row % resid_mod (broadcast of pos_embed over the frame batch)
+  const int* skip = nullptr;     // device flag: != 0 -> the whole kernel returns at once (the mask decoder's on-device break)
 };
 
 // K-loop segments for split precision: segment i multiplies A[:, a_off[i] : a_off[i]+K] with B[:, b_off[i] : b_off[i]+K]

@@ -127,6 +127,19 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// x16 load into elements [OFF, OFF+16) of a larger register array (keeps the array in registers: no pointer casts)
+template <int OFF, int N>
+__device__ __forceinline__ void tmem_ld16_at(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(OFF + 16 <= N, "tmem_ld16_at: out of range");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[OFF + 0]), "=r"(r[OFF + 1]), "=r"(r[OFF + 2]), "=r"(r[OFF + 3]), "=r"(r[OFF + 4]), "=r"(r[OFF + 5]), "=r"(r[OFF + 6]),
+        "=r"(r[OFF + 7]), "=r"(r[OFF + 8]), "=r"(r[OFF + 9]), "=r"(r[OFF + 10]), "=r"(r[OFF + 11]), "=r"(r[OFF + 12]),
+        "=r"(r[OFF + 13]), "=r"(r[OFF + 14]), "=r"(r[OFF + 15])
+      : "r"(taddr)
+      : "memory");
+}
 // registers -> TMEM: 32 lanes x 32 bit, 16 consecutive columns (thread = TMEM lane, register j = column j)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(

@@ -108,7 +108,11 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
   // two (weights split).  Their activations are bounded by the fp16 attention path anyway: qkv's OUTPUT is rounded to
   // fp16 for the attention operands and proj's INPUT is the fp16-P x fp16-V attention output, so the A_lo.W_hi pass would add
   // precision that the neighbouring fp16 rounding discards.  precision 4 = all GEMMs three passes.
-  const int p_attn = precision == 3 ? 2 : (precision >= 4 ? 3 : precision);
+  // precision 5: like 3, but the attention OUTPUT is carried as fp16 hi|lo and the proj GEMM runs all three passes -- the
+  // attention kernel accumulates O in fp32, so this removes the 2^-11 rounding of proj's input; qkv stays at two passes (its
+  // output is rounded to fp16 for the attention operands whatever the GEMM does).
+  const int p_qkv = (precision == 3 || precision == 5) ? 2 : (precision >= 4 ? 3 : precision);
+  const int p_proj = precision == 3 ? 2 : (precision >= 4 ? 3 : precision);
   if (precision >= 4) precision = 3;
   const int asp = precision >= 3 ? 2 : 1;  // A operands (activations) carried as hi|lo
   const int bsp = precision >= 2 ? 2 : 1;  // B operands (weights) carried as hi|lo
@@ -157,7 +161,7 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
   bool save_const = false;    // this call runs in full and saves the constant rows before block fg
   if (pad_candidate) {
     char key[160];
-    snprintf(key, sizeof(key), "vitconst:%dx%d:g%d:w%d:d%d:D%d:fg%d:p%d", Hr, Wr, G, ws, d.depth, D, fg, precision * 10 + p_attn);
+    snprintf(key, sizeof(key), "vitconst:%dx%d:g%d:w%d:d%d:D%d:fg%d:p%d", Hr, Wr, G, ws, d.depth, D, fg, precision * 100 + p_qkv * 10 + p_proj);
     auto it = c->owned.find(key);
     if (it == c->owned.end()) {
       void* buf = nullptr;
@@ -234,21 +238,21 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
     const int Lkp = is_global ? GG : Lkpw;
     const int NT = is_global ? 128 : (((Lw + 15) / 16) * 16 <= 256 ? ((Lw + 15) / 16) * 16 : 128);
     // LN1 (+ window partition with zero padding)
-    SAMPT_TRY(ln_rows(c, st, x, D, is_global ? nullptr : blk_wmap, n1w, n1b, 1e-6f, A, D * asp, (asp == 2 && p_attn == 3) ? D : 0, Mrows, D, 1));
+    SAMPT_TRY(ln_rows(c, st, x, D, is_global ? nullptr : blk_wmap, n1w, n1b, 1e-6f, A, D * asp, (asp == 2 && p_qkv == 3) ? D : 0, Mrows, D, 1));
     // qkv = Linear(D, 3D)
     {
       GemmEpi ep{};
       ep.out16 = qkv; ep.bias = qkvb; ep.ldc = 3 * D;
-      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wqkv, D * bsp, Mrows, 3 * D, D, make_seg(p_attn, D), ep));
+      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wqkv, D * bsp, Mrows, 3 * D, D, make_seg(p_qkv, D), ep));
     }
     // attention
     SAMPT_TRY(attn_prep(c, st, qkv, 3 * D, rph, rpw, Qx, Kx, Vt, nwb, d.nheads, S, Lkp, DK, D, HD, 1.0f / sqrtf((float)HD)));
-    SAMPT_TRY(attn_tc(c, st, Qx, Kx, Vt, nwb * d.nheads, L, L, Lkp, DK, HD, NT, d.nheads, att, D * asp, (asp == 2 && p_attn == 3) ? D : 0));
+    SAMPT_TRY(attn_tc(c, st, Qx, Kx, Vt, nwb * d.nheads, L, L, Lkp, DK, HD, NT, d.nheads, att, D * asp, (asp == 2 && p_proj == 3) ? D : 0));
     // x = x + proj(attn)   (window un-partition via the row map; padding rows are dropped)
     {
       GemmEpi ep{};
       ep.out32 = x; ep.resid = x; ep.bias = projb; ep.ldc = D; ep.rowmap = is_global ? nullptr : blk_wmap;
-      SAMPT_TRY(gemm_tc(c, st, att, D * asp, wproj, D * bsp, Mrows, D, D, make_seg(p_attn, D), ep));
+      SAMPT_TRY(gemm_tc(c, st, att, D * asp, wproj, D * bsp, Mrows, D, D, make_seg(p_proj, D), ep));
     }
     // x = x + lin2(gelu(lin1(LN2(x))))
     SAMPT_TRY(ln_rows(c, st, x, D, live_only ? tmap_c : nullptr, n2w, n2b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mmlp, D, 1));
@@ -305,7 +309,7 @@ extern "C" int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B
                                 int patch_size, int out_chans, int precision, const float* pixel_mean_host,
                                 const float* pixel_std_host, float* features, float* interm, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
-  SAMPT_CHECK(precision >= 1 && precision <= 4, "sampt_vit_encode: precision must be 1..4");
+  SAMPT_CHECK(precision >= 1 && precision <= 5, "sampt_vit_encode: precision must be 1..5");
   SAMPT_CHECK(img_size % patch_size == 0, "img_size must be a multiple of patch_size");
   SAMPT_CHECK(Hr <= img_size && Wr <= img_size, "resized image (%dx%d) exceeds img_size %d", Hr, Wr, img_size);
   SAMPT_CHECK(embed_dim % 128 == 0 && embed_dim % num_heads == 0, "embed_dim must be a multiple of 128 and of num_heads");
@@ -319,7 +323,7 @@ extern "C" int sampt_vit_encode_f32(sampt_ctx* ctx, const float* x, int B, int d
                                     const int* global_idx_host, int n_global, int img_size, int patch_size, int out_chans,
                                     int precision, float* features, float* interm, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
-  SAMPT_CHECK(precision >= 1 && precision <= 4, "sampt_vit_encode_f32: precision must be 1..4");
+  SAMPT_CHECK(precision >= 1 && precision <= 5, "sampt_vit_encode_f32: precision must be 1..5");
   SAMPT_CHECK(img_size % patch_size == 0, "img_size must be a multiple of patch_size");
   SAMPT_CHECK(embed_dim % 128 == 0 && embed_dim % num_heads == 0, "embed_dim must be a multiple of 128 and of num_heads");
   VitDims d{depth, embed_dim, num_heads, window_size, img_size / patch_size, patch_size, out_chans};

@@ -73,7 +73,7 @@ class ImageEncoderViT(nn.Module):
         if self._registered != key or not ctx.owns("sam.image_encoder", self):
             torch.cuda.synchronize(dev)  # nothing may still be reading the tensors this replaces
             native.check(native.lib().sampt_vit_cache_clear(ctx.handle), "vit_cache_clear")  # rows saved for the old weights
-            split_b = self.precision >= 2
+            split_b = self.precision >= 2   # (3, 4, 5: activations split as well, decided inside sampt_vit_encode)
             sd = self.state_dict()
             D = self.embed_dim
             ctx.set_tensor(prefix + "patch_embed.w16", self._w16(sd["patch_embed.proj.weight"].reshape(D, -1), split_b))

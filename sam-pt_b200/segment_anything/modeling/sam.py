@@ -68,6 +68,19 @@ class Sam(nn.Module):
         w0 = sd["output_upscaling.0.weight"].float()
         ctx.set_tensor("sam.mask_decoder.output_upscaling.0.weight_gemm", w0.permute(2, 3, 1, 0).reshape(-1, w0.shape[0]))
         ctx.set_tensor("sam.mask_decoder.output_upscaling.0.bias4", sd["output_upscaling.0.bias"].float().repeat(4))
+
+        # image-side projections (4096-row operands) run on the tcgen05 GEMM with the 3-pass fp16 hi|lo split (~fp32 products):
+        # weights as [N, 2K] = hi | lo
+        def w16(wm):
+            wm = wm.float()
+            hi = wm.half()
+            return torch.cat([hi, (wm - hi.float()).half()], dim=1).contiguous()
+
+        ctx.set_tensor("sam.mask_decoder.output_upscaling.0.w16", w16(w0.permute(2, 3, 1, 0).reshape(-1, w0.shape[0])))
+        for name in [f"transformer.layers.{i}.cross_attn_token_to_image.{p}_proj" for i in range(2) for p in ("k", "v")] + \
+                    [f"transformer.layers.{i}.cross_attn_image_to_token.{p}_proj" for i in range(2) for p in ("q", "out")] + \
+                    [f"transformer.final_attn_token_to_image.{p}_proj" for p in ("k", "v")]:
+            ctx.set_tensor(f"sam.mask_decoder.{name}.w16", w16(sd[name + ".weight"]))
         # key positional encoding folded through the (linear) k/q projections that consume `keys + key_pe`
         dense_pe = pe.get_dense_pe()[0].flatten(1).t().contiguous()  # (h*w, 256) token-major
         ctx.set_tensor("sam.dense_pe_tok", dense_pe)

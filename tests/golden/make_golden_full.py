@@ -105,8 +105,10 @@ def main():
 
         def tracker(im, q):
             t0 = time.time()
-            out = cotracker_ref.cotracker_point_tracker_forward(cot_sd, im, q)
+            raw = {}
+            out = cotracker_ref.cotracker_point_tracker_forward(cot_sd, im, q, raw=raw)
             box["t"] = box.get("t", 0.0) + time.time() - t0
+            box.setdefault("vis_sigmoid", []).append(raw["vis_sigmoid"][0])      # (T, m*P) per mask batch
             return out
         pips_sd_arg = None
 
@@ -156,7 +158,9 @@ def main():
     np.savez_compressed(out, trajectories=ref["trajectories"].numpy(), visibilities=ref["visibilities"].numpy(),
                         scores_per_frame=np.array(ref["scores_per_frame"], dtype=np.float32), mask_bits=bits,
                         logit_stats=stats.astype(np.float32), n_refine=n_ref, query_points=video["query_points"].numpy(),
-                        hw=np.array([c["H"], c["W"]]))
+                        hw=np.array([c["H"], c["W"]]),
+                        vis_sigmoid=(torch.cat(box["vis_sigmoid"], dim=1).reshape(T, -1, c["P"]).numpy()
+                                     if c["tracker"] == "cotracker" else np.zeros((0,), dtype=np.float32)))
     meta = {"config": args.config, **{k: c[k] for k in ("T", "H", "W", "P", "tracker", "hq", "seed", "keep")},
             "frames_run": T, "seconds": secs, "frames_per_s": T / secs["total"], "threads": args.threads, "cpu": cpu_model(),
             "calibration_sample": sample, "sam_seed": SAM_SEED, "tracker_seed": PIPS_SEED if c["tracker"] == "pips" else PIPS_SEED + 1,
