@@ -18,8 +18,12 @@ def val(r, name):
 
 
 out = {}
-for key in ("gemm_tc_kernel", "pips_corr"):
-    rs = [r for r in data if key in r[col["Kernel Name"]]]
+KEYS = {"gemm_tc_kernel": lambda n, r: "gemm_tc" in n, "pips_corr": lambda n, r: "pips_corr" in n,
+        # the two attention launches of tools/ncu_targets.py: the windowed one has 4000 items (grid 148), told apart by duration
+        "attn_windowed": lambda n, r: "attn_ws" in n and val(r, "gpu__time_duration.sum") < 800.0,
+        "attn_global": lambda n, r: "attn_ws" in n and val(r, "gpu__time_duration.sum") >= 800.0}
+for key, pred in KEYS.items():
+    rs = [r for r in data if pred(r[col["Kernel Name"]], r)]
     if not rs:
         continue
     rd = [val(r, "dram__bytes_read.sum") for r in rs]

@@ -45,7 +45,6 @@ int resize_ac_concat(Ctx* c, cudaStream_t st, const float* in, float* out, int N
 int avgpool2_nhwc(Ctx* c, cudaStream_t st, const float* in, float* out, int Nimg, int Hi, int Wi, int C);
 int pips_window_init(Ctx* c, cudaStream_t st, const PipsWin& w);
 int pips_corr(Ctx* c, cudaStream_t st, const PipsWin& w, float* xin, int ldx);
-int pips_corr_only(Ctx* c, cudaStream_t st, const PipsWin& w, float* fcorr);
 int mixer_token(Ctx* c, cudaStream_t st, float* x, float* xln, const uint8_t* active, int N, const float* ln_w,
                 const float* ln_b, const float* w1, const float* b1, const float* w2, const float* b2, const float* ln2_w,
                 const float* ln2_b, int do_token_mix);
@@ -67,6 +66,8 @@ int ln_rows(Ctx* c, cudaStream_t st, const float* x, int ldx, const int* src, co
             __half* out, int ldo, int split_off, int Mout, int D, int normalize);
 int attn_prep(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* relh, const float* relw, __half* Qx, __half* Kx,
               __half* Vt, int nwb, int nheads, int S, int Lkp, int DK, int D, int HD, float scale);
+int attn_prep2(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* relh, const float* relw, __half* Qx, __half* Kx,
+               __half* Vt, int nwb, int nheads, int S, int Lkp, int DK, int D, int HD, float scale);
 int neck_ln_im2col(Ctx* c, cudaStream_t st, const float* y1, const float* gamma, const float* beta, __half* A, int B, int G, int C,
                    int ld, int split_off);
 int neck_ln_nchw(Ctx* c, cudaStream_t st, const float* y2, const float* gamma, const float* beta, float* out, int B, int GG, int C);

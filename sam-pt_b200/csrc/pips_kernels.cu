@@ -610,63 +610,6 @@ pips_corr_kernel(PipsWin w, float* __restrict__ xin, int ldx) {
   if (t == 3) row[519] = 0.f;
 }
 
-// stand-alone variant for the parity test of the "first kernel" (SURVEY §7.3): writes only fcorrs (N,S,196)
-__global__ void __launch_bounds__(256)
-pips_corr_only_kernel(PipsWin w, float* __restrict__ fcorr) {
-  // identical gather path; see pips_corr_kernel.  Kept separate so the unit test measures exactly the lookup.
-  const int n = blockIdx.x / w.S, s = blockIdx.x % w.S;
-  __shared__ float D[4][64];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* ff = w.ffeats + ((size_t)n * w.S + s) * 128;
-  const float4 q = *reinterpret_cast<const float4*>(ff + lane * 4);
-  const float cx0 = w.coords[((size_t)n * w.S + s) * 2 + 0];
-  const float cy0 = w.coords[((size_t)n * w.S + s) * 2 + 1];
-  const int fi = w.wp[2 + s];
-#pragma unroll
-  for (int l = 0; l < 4; ++l) {
-    const int H = w.H[l], W = w.W[l];
-    const float sc = 1.0f / (float)(1 << l);
-    const float cx = cx0 * sc, cy = cy0 * sc;
-    const int bx = (int)floorf(cx) - 3, by = (int)floorf(cy) - 3;
-    const float* fm = w.pyr[l] + (size_t)fi * H * W * 128;
-    float part[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int pidx = warp * 8 + j;
-      int py = by + (pidx >> 3), px = bx + (pidx & 7);
-      float d = 0.f;
-      if (py >= 0 && py < H && px >= 0 && px < W) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(fm + ((size_t)py * W + px) * 128 + lane * 4));
-        d = q.x * v.x + q.y * v.y + q.z * v.z + q.w * v.w;
-      }
-      part[j] = d;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float d = warp_sum(part[j]);
-      if (lane == 0) D[l][warp * 8 + j] = d * 0.08838834764831845f;
-    }
-  }
-  __syncthreads();
-  const int t = threadIdx.x;
-  if (t < 196) {
-    int l = t / 49, r = t % 49, a = r / 7, b = r % 7;
-    const float sc = 1.0f / (float)(1 << l);
-    const float cx = cx0 * sc, cy = cy0 * sc;
-    const int H = w.H[l], W = w.W[l];
-    float sx = cx + (float)(a - 3), sy = cy + (float)(b - 3);
-    float gx = 2.0f * sx / (float)(W - 1) - 1.0f, gy = 2.0f * sy / (float)(H - 1) - 1.0f;
-    float ux = ((gx + 1.0f) * 0.5f) * (float)(W - 1), uy = ((gy + 1.0f) * 0.5f) * (float)(H - 1);
-    float x0f = floorf(ux), y0f = floorf(uy);
-    float fx = ux - x0f, fy = uy - y0f;
-    const int bx = (int)floorf(cx) - 3, by = (int)floorf(cy) - 3;
-    int ix = (int)x0f - bx, iy = (int)y0f - by;
-    auto at = [&](int yy, int xx) -> float { return (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) ? D[l][yy * 8 + xx] : 0.f; };
-    float v = (1.f - fx) * (1.f - fy) * at(iy, ix) + fx * (1.f - fy) * at(iy, ix + 1) + (1.f - fx) * fy * at(iy + 1, ix) +
-              fx * fy * at(iy + 1, ix + 1);
-    fcorr[((size_t)n * w.S + s) * 196 + t] = v;
-  }
-}
 
 int pips_window_init(Ctx* c, cudaStream_t st, const PipsWin& w) {
   pips_window_init_kernel<<<w.N, 128, 0, st>>>(w);
@@ -676,12 +619,6 @@ int pips_window_init(Ctx* c, cudaStream_t st, const PipsWin& w) {
 }
 int pips_corr(Ctx* c, cudaStream_t st, const PipsWin& w, float* xin, int ldx) {
   pips_corr_kernel<<<w.N * w.S, 256, 0, st>>>(w, xin, ldx);
-  c->launches++;
-  SAMPT_LAUNCH_CHECK();
-  return 0;
-}
-int pips_corr_only(Ctx* c, cudaStream_t st, const PipsWin& w, float* fcorr) {
-  pips_corr_only_kernel<<<w.N * w.S, 256, 0, st>>>(w, fcorr);
   c->launches++;
   SAMPT_LAUNCH_CHECK();
   return 0;

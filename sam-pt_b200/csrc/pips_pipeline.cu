@@ -528,5 +528,17 @@ extern "C" int sampt_pips_corr_lookup(sampt_ctx* ctx, const float* fmaps, const 
   for (int l = 1; l < 4; ++l) { w.H[l] = w.H[l - 1] / 2; w.W[l] = w.W[l - 1] / 2; }
   w.coords = const_cast<float*>(coords);
   w.ffeats = const_cast<float*>(ffeats);
-  return pips_corr_only(c, st, w, fcorr);
+  // the PRODUCT kernel (pips_corr_kernel: gather + mixer-row assembly), then the 196 correlation columns of its [N*S, 520] rows are
+  // copied out -- the unit test and bench.py's roofline entry exercise exactly the kernel the tracker runs
+  uint8_t* active_d; float *traj_d, *xin;
+  SAMPT_TRY(ws_get(c, &active_d, (size_t)N, "active"));
+  SAMPT_TRY(ws_get(c, &traj_d, (size_t)N * 2, "traj"));
+  SAMPT_TRY(ws_get(c, &xin, (size_t)N * S * 520, "xin"));
+  SAMPT_CUDA(cudaMemsetAsync(active_d, 1, (size_t)N, st));
+  SAMPT_CUDA(cudaMemsetAsync(traj_d, 0, (size_t)N * 2 * sizeof(float), st));
+  w.active = active_d; w.traj = traj_d;
+  SAMPT_TRY(pips_corr(c, st, w, xin, 520));
+  SAMPT_CUDA(cudaMemcpy2DAsync(fcorr, 196 * sizeof(float), xin + 128, 520 * sizeof(float), 196 * sizeof(float), (size_t)N * S,
+                               cudaMemcpyDeviceToDevice, st));
+  return 0;
 }

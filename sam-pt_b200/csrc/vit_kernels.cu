@@ -347,6 +347,10 @@ attn_prep_kernel(const __half* __restrict__ qkv, int ldq, const float* __restric
 }
 int attn_prep(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* relh, const float* relw, __half* Qx, __half* Kx,
               __half* Vt, int nwb, int nheads, int S, int Lkp, int DK, int D, int HD, float scale) {
+  {   // round-2 kernel (attn_prep2.cu: rel-pos products on the tensor cores); falls through for shapes it does not cover
+    const int rc = attn_prep2(c, st, qkv, ldq, relh, relw, Qx, Kx, Vt, nwb, nheads, S, Lkp, DK, D, HD, scale);
+    if (rc <= 0) return rc;
+  }
   const int L = S * S;
   const int TC = (S == 14) ? 200 : 64;  // one whole 14x14 window (padded to a multiple of 8) or one row of the 64x64 grid
   SAMPT_CHECK(HD == 80 || HD == 64, "attn_prep: head_dim %d not built (80 = ViT-H, 64 = ViT-B/L/test)", HD);

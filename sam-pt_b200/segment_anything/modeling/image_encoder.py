@@ -13,13 +13,15 @@ from torch import nn
 from sampt_b200 import native
 from sampt_b200.param_tree import build_param_tree
 
-# GEMM accuracy dial (DESIGN.md "precision"): 1 = fp16 operands single pass; 2 = WEIGHTS carried as fp16 hi|lo (exact
-# weights, fp16-rounded activations; 2 tensor-core passes); 3 = activations carried as hi|lo too (~fp32, 3 passes).
-# 3 is "mixed": qkv / proj GEMMs use 2 passes (their activations are fp16-limited by the attention path), the MLP GEMMs 3;
-# 4 = three passes everywhere.
-# Measured on C1 against the oracle: weight rounding is the coherent error that moves masks; activation rounding averages
-# out (IoU 0.9986 / see gpurun precision_dial / 0.99996 for 1 / 2 / 3).
-DEFAULT_PRECISION = int(os.environ.get("SAMPT_VIT_PRECISION", "3"))
+# GEMM accuracy dial (DESIGN.md "precision"): operands are carried as fp16 hi | lo (lo = fp16(x - hi)) and the tcgen05 K loop runs
+# over up to three segments A_hi.B_hi + A_lo.B_hi + A_hi.B_lo into one fp32 TMEM accumulator.
+#   1 = fp16 x fp16, one pass          2 = weights hi|lo, two passes          3 = MLP three passes, qkv / proj two
+#   5 = MLP + proj three passes (attention output kept as hi|lo), qkv two     4 = three passes everywhere (~fp32 products)
+# Measured on the B200 against the FULL BASELINE clips (tests/test_gpu_full_configs.py, 50 frames of C2 / 8 of the C5 slice; bar:
+# per-frame IoU >= 0.999):  3: min IoU 0.99878 / 0.99873 (fails);  5: 0.99911 / 0.99951 (one frame of C2 within 1e-4 of the bar);
+# 4: 0.99979 / 0.99961.  With random weights the mask logits are noise-like, the 12-step box refinement amplifies a 1-pixel box
+# change into ~1e-3 IoU, so the default is 4: parity first.  5 / 3 are the faster modes (+4 % / +7 % frames/s), never the headline.
+DEFAULT_PRECISION = int(os.environ.get("SAMPT_VIT_PRECISION", "4"))
 
 
 class ImageEncoderViT(nn.Module):

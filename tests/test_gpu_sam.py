@@ -175,34 +175,25 @@ def test_precision_dial_report(tmp_path):
     assert min(report[3]) >= 0.999
 
 
-def test_sampt_c2_slice_vit_h(tmp_path):
-    """BASELINE config C2's model and resolution (SAM ViT-H + PIPS, 480x854, 8 points, 12 refinements) on the first 2 frames
-    of the C2 clip (the CPU oracle needs ~12 s per ViT-H frame): coords within 1e-3 px, per-frame IoU >= 0.999."""
-    cfg = sam_ref.VIT_H
-    sam_sd = _sam_sd(cfg, 7202)
-    pips_sd = synth.condition_pips(synth.make_state_dict(pips_ref.pips_state_dict_shapes(), 7201))
-    ckpt = synth.write_pips_checkpoint_dir(pips_sd, str(tmp_path / "pips"))
-    video = synth.make_video_dict(50, 480, 854, 8)
-    video["image"] = video["image"][:2]
-    ref = sampt_ref.sampt_forward(pips_sd, sam_ref.RefSamPredictor(sam_sd, cfg), video, positive_points_per_mask=8,
-                                  sam_iou_threshold=-1e9)
-    model = factory.build_sam_pt("vit_h", sam_sd, ckpt, positive_points_per_mask=8, sam_iou_threshold=-1e9)
-    out = model(video)
-    assert (out["trajectories"].cpu() - ref["trajectories"]).abs().max() < 1e-3
-    assert torch.equal(out["visibilities"].cpu(), ref["visibilities"])
-    ious = [_iou(out["logits"][0][f].cpu(), ref["logits"][0][f]) for f in range(2)]
-    import json
-    import os
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
-    rep = {"default_precision": model.sam_predictor.model.image_encoder.precision, "iou": ious}
-    for p in (1, 2, 4):
-        model.sam_predictor.model.image_encoder.precision = p
-        o = model(video)
-        rep[f"iou_precision_{p}"] = [_iou(o["logits"][0][f].cpu(), ref["logits"][0][f]) for f in range(2)]
-    with open(os.path.join(root, "gpurun_out", "precision_dial_c2slice.json"), "w") as fh:
-        json.dump(rep, fh)
-    assert min(ious) >= 0.999, ious
+# (the 2-frame C2 slice of round 1 is superseded by tests/test_gpu_full_configs.py: all 50 frames of C2 against the full-clip golden)
+
+
+def test_image_encoder_forward_float_interface():
+    """upstream `ImageEncoderViT.forward(x)`: x = Sam.preprocess output (normalised, zero-padded float image) -> (B,256,64,64)."""
+    cfg = ORACLE_CFG["vit_test"]
+    sd = _sam_sd(cfg, 31)
+    sam = factory.build_sam("vit_test", sd).cuda()
+    clip = synth.make_clip(2, 240, 320, seed=3)
+    xs = torch.cat([sam_ref.preprocess(clip["frames"][b].permute(1, 2, 0).numpy())[0] for b in range(2)], dim=0)   # (2,3,1024,1024)
+    got = sam.image_encoder(xs.cuda()).cpu()
+    for b in range(2):
+        ref = sam_ref.vit_encode(sd, xs[b:b + 1], cfg)[0]
+        rel = ((got[b] - ref).norm() / ref.norm()).item()
+        assert rel < 3e-4, rel
+    # and it agrees with the fused uint8 path SamPredictor uses
+    from segment_anything.predictor import SamPredictor
+    feats = SamPredictor(sam).encode_frames(clip["frames"].cuda()).cpu()
+    assert ((feats - got).norm() / got.norm()).item() < 1e-4
 
 
 # ---------------------------------------------------------------------------------------------------------------- HQ-SAM
