@@ -34,12 +34,42 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// grid (chunks of TC tokens, heads, windows*frames); 256 threads.  TC % 16 == 0.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// Rcat = [Rh ; Rw] (2(2S-1) rows, zero padded to NRP) as fp16 hi | lo tables with the shared-memory row pitch QP, built once per
+// launch so that every CTA fetches it with plain 16-byte asynchronous copies
 template <int HD>
-__global__ void __launch_bounds__(256)
-attn_prep2_kernel(const __half* __restrict__ qkv, int ldq, const float* __restrict__ relh, const float* __restrict__ relw,
-                  __half* __restrict__ Qx, __half* __restrict__ Kx, __half* __restrict__ Vt, int S, int L, int Lkp, int DK, int D,
-                  int nheads, float scale, int TC, int NRP /* padded table rows: multiple of 8 >= 2(2S-1) */) {
+__global__ void relpos_table_kernel(const float* __restrict__ relh, const float* __restrict__ relw, __half* __restrict__ tab, int S,
+                                    int NRP) {
+  constexpr int QP = HD + 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NRP * QP) return;
+  const int r = i / QP, d = i % QP;
+  float v = 0.f;
+  if (d < HD) {
+    if (r < 2 * S - 1) v = relh[(size_t)r * HD + d];
+    else if (r < 2 * (2 * S - 1)) v = relw[(size_t)(r - (2 * S - 1)) * HD + d];
+  }
+  const __half hi = __float2half_rn(v);
+  tab[i] = hi;
+  tab[(size_t)NRP * QP + i] = __float2half_rn(v - __half2float(hi));
+}
+
+// grid (chunks of TC tokens, heads, windows*frames); 256 threads.  TC % 16 == 0.
+// All global loads of a CTA (q and v tiles, the table) are issued up front as cp.async 16-byte copies and overlap with the K' rows,
+// which are copied global -> global through registers in batches of four independent loads; V^T leaves in 128-byte runs.
+template <int HD>
+__global__ void __launch_bounds__(256, 2)
+attn_prep2_kernel(const __half* __restrict__ qkv, int ldq, const __half* __restrict__ tab, __half* __restrict__ Qx,
+                  __half* __restrict__ Kx, __half* __restrict__ Vt, int S, int L, int Lkp, int DK, int D, int nheads, float scale, int TC,
+                  int NRP /* padded table rows: multiple of 8 >= 2(2S-1) */) {
   constexpr int QP = HD + 8;            // row pitch in halves: 16 B aligned, conflict-free for ldmatrix
   constexpr int KS = HD / 16;           // k-steps of the MMA
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -56,37 +86,40 @@ attn_prep2_kernel(const __half* __restrict__ qkv, int ldq, const float* __restri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t bh = (size_t)wb * nheads + h;
   constexpr int SEG = HD / 8;           // 16-byte segments per head row
-  const int NR = 2 * (2 * S - 1);
+  const __half* gq = qkv + ((size_t)wb * L + t0) * ldq + h * HD;
 
-  // ---- phase 1: coalesced 16 B loads of q / k / v head rows.  k goes straight back out as the dot part of K'.
+  // ---- phase 1: asynchronous copies of q, v and the table into shared memory; rows beyond nt are zeroed
   for (int i = tid; i < TC * SEG; i += 256) {
     const int t = i / SEG, sgm = i % SEG;
-    uint4 qv = make_uint4(0u, 0u, 0u, 0u), vv = make_uint4(0u, 0u, 0u, 0u);
     if (t < nt) {
-      const __half* rowp = qkv + (size_t)((size_t)wb * L + t0 + t) * ldq + h * HD + sgm * 8;
-      qv = *reinterpret_cast<const uint4*>(rowp);
-      const uint4 kv = *reinterpret_cast<const uint4*>(rowp + D);
-      vv = *reinterpret_cast<const uint4*>(rowp + 2 * D);
-      *reinterpret_cast<uint4*>(Kx + (bh * L + t0 + t) * DK + sgm * 8) = kv;
+      cp_async16(sq + (size_t)t * QP + sgm * 8, gq + (size_t)t * ldq + sgm * 8);
+      cp_async16(sv + (size_t)t * QP + sgm * 8, gq + (size_t)t * ldq + 2 * D + sgm * 8);
+    } else {
+      *reinterpret_cast<uint4*>(sq + (size_t)t * QP + sgm * 8) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(sv + (size_t)t * QP + sgm * 8) = make_uint4(0u, 0u, 0u, 0u);
     }
-    *reinterpret_cast<uint4*>(sq + (size_t)t * QP + sgm * 8) = qv;
-    *reinterpret_cast<uint4*>(sv + (size_t)t * QP + sgm * 8) = vv;
   }
-  // Rcat = [Rh ; Rw] as fp16 hi / lo (rows >= NR zero)
-  for (int i = tid; i < NRP * HD; i += 256) {
-    const int r = i / HD, d = i % HD;
-    float v = 0.f;
-    if (r < 2 * S - 1) v = relh[(size_t)r * HD + d];
-    else if (r < NR) v = relw[(size_t)(r - (2 * S - 1)) * HD + d];
-    const __half hi = __float2half_rn(v);
-    sRh[(size_t)r * QP + d] = hi;
-    sRl[(size_t)r * QP + d] = __float2half_rn(v - __half2float(hi));
-  }
-  // K' extension: one-hots of (ky, kx) + zero padding, 16 B at a time
-  const int EXT = DK - HD;
-  for (int i = tid; i < TC * (EXT / 8); i += 256) {
-    const int t = i / (EXT / 8), e0 = (i % (EXT / 8)) * 8;
-    if (t < nt) {
+  for (int i = tid; i < 2 * NRP * QP / 8; i += 256) cp_async16(sRh + (size_t)i * 8, tab + (size_t)i * 8);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // ---- phase 2 (overlaps the copies): K' rows = [k | onehot(ky) | onehot(kx) | 0], global -> global
+  {
+    const int n_items = nt * SEG;
+    for (int i0 = tid; i0 < n_items; i0 += 4 * 256) {
+      uint4 kv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < n_items) kv[u] = *reinterpret_cast<const uint4*>(gq + (size_t)(i / SEG) * ldq + D + (i % SEG) * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < n_items) *reinterpret_cast<uint4*>(Kx + (bh * L + t0 + i / SEG) * DK + (i % SEG) * 8) = kv[u];
+      }
+    }
+    const int EXT = DK - HD;
+    for (int i = tid; i < nt * (EXT / 8); i += 256) {
+      const int t = i / (EXT / 8), e0 = (i % (EXT / 8)) * 8;
       const int tt = t0 + t, ty = tt / S, tx = tt % S;
       __half hv[8];
 #pragma unroll
@@ -97,30 +130,38 @@ attn_prep2_kernel(const __half* __restrict__ qkv, int ldq, const float* __restri
       *reinterpret_cast<uint4*>(Kx + (bh * L + tt) * DK + HD + e0) = *reinterpret_cast<uint4*>(hv);
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  // ---- phase 2: V^T -- thread = (d, group of 8 consecutive tokens) -> one 16 B store
+  // ---- phase 3: V^T.  A warp writes 4 rows d x 8 groups of 8 keys: 4 runs of 128 contiguous bytes per store instruction; the
+  //      8 values of a group are read in a lane-rotated order so that the 8 lanes of a run hit 8 different banks
   {
     const int ngrp = (TC + 7) / 8;
-    for (int i = tid; i < HD * ngrp; i += 256) {
-      const int g = i / HD, d = i % HD;  // consecutive threads -> consecutive d: conflict-free shared-memory reads
-      __half hv[8];
+    const int ngrp8 = (ngrp + 7) / 8;                 // groups are handed out 8 at a time
+    for (int w = warp; w < (HD / 4) * ngrp8; w += 8) {
+      const int d = (w / ngrp8) * 4 + (lane >> 3);
+      const int g = (w % ngrp8) * 8 + (lane & 7);
+      if (g < ngrp) {
+        __half hv[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int t = g * 8 + j;
-        hv[j] = (t < nt) ? sv[(size_t)t * QP + d] : __float2half_rn(0.f);
+        for (int j = 0; j < 8; ++j) {
+          const int jj = (j + (lane & 7)) & 7;
+          const int t = g * 8 + jj;
+          hv[jj] = (t < nt) ? sv[(size_t)t * QP + d] : __float2half_rn(0.f);
+        }
+        if (t0 + g * 8 < Lkp) *reinterpret_cast<uint4*>(Vt + (bh * HD + d) * Lkp + t0 + g * 8) = *reinterpret_cast<uint4*>(hv);
       }
-      if (t0 + g * 8 < Lkp) *reinterpret_cast<uint4*>(Vt + (bh * HD + d) * Lkp + t0 + g * 8) = *reinterpret_cast<uint4*>(hv);
     }
-    if (t0 + TC >= L) {   // tile padding of V^T (keys in [L, Lkp)) beyond the last written group: zeros, written by the last chunk
+    if (t0 + TC >= L) {   // tile padding of V^T (keys in [L, Lkp)) beyond the last written group: zeros, 16 B at a time
       const int first = ((L - t0 + 7) / 8) * 8 + t0;
-      for (int i = tid; i < HD * max(0, Lkp - first); i += 256) {
-        const int d = i / (Lkp - first), t = first + i % (Lkp - first);
-        Vt[(bh * HD + d) * Lkp + t] = __float2half_rn(0.f);
+      const int npad8 = max(0, Lkp - first) / 8;
+      for (int i = tid; i < HD * npad8; i += 256) {
+        const int d = i / npad8, t = first + (i % npad8) * 8;
+        *reinterpret_cast<uint4*>(Vt + (bh * HD + d) * Lkp + t) = make_uint4(0u, 0u, 0u, 0u);
       }
     }
   }
   __syncthreads();   // sv is dead from here: T goes over it
-  // ---- phase 3: T[TC x NRP] = q . Rcat^T on the tensor cores (mma.sync m16n8k16, fp32 accumulate, Rcat = hi + lo)
+  // ---- phase 4: T[TC x NRP] = q . Rcat^T on the tensor cores (mma.sync m16n8k16, fp32 accumulate, Rcat = hi + lo)
   {
     const int mt = TC / 16, ntile = NRP / 8;
     for (int m = warp; m < mt; m += 8) {
@@ -146,23 +187,32 @@ attn_prep2_kernel(const __half* __restrict__ qkv, int ldq, const float* __restri
     }
   }
   __syncthreads();
-  // ---- phase 4: Q' rows, 16 B per thread-step: [q*scale (HD) | T[t][ty - j + S-1] (S) | T[t][(2S-1) + tx - j + S-1] (S) | 0]
+  // ---- phase 5: Q' rows, 16 B per thread-step: [q*scale (HD) | T[t][ty - j + S-1] (S) | T[t][(2S-1) + tx - j + S-1] (S) | 0]
   {
     const int cpr = DK / 8;  // 16-byte chunks per row
-    for (int i = tid; i < TC * cpr; i += 256) {
+    for (int i = tid; i < nt * cpr; i += 256) {
       const int t = i / cpr, c8 = (i % cpr) * 8;
-      if (t >= nt) continue;
       const int tt = t0 + t, ty = tt / S, tx = tt % S;
       __half hv[8];
+      if (c8 + 8 <= HD) {
+        const uint4 qv = *reinterpret_cast<const uint4*>(sq + (size_t)t * QP + c8);
+        const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int col = c8 + j;
-        __half v;
-        if (col < HD) v = __float2half_rn(__half2float(sq[(size_t)t * QP + col]) * scale);
-        else if (col < HD + S) v = sT[(size_t)t * TP + (ty - (col - HD) + S - 1)];
-        else if (col < HD + 2 * S) v = sT[(size_t)t * TP + (2 * S - 1) + (tx - (col - HD - S) + S - 1)];
-        else v = __float2half_rn(0.f);
-        hv[j] = v;
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(q2[j]);
+          reinterpret_cast<__half2*>(hv)[j] = __floats2half2_rn(f.x * scale, f.y * scale);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = c8 + j;
+          __half v;
+          if (col < HD) v = __float2half_rn(__half2float(sq[(size_t)t * QP + col]) * scale);
+          else if (col < HD + S) v = sT[(size_t)t * TP + (ty - (col - HD) + S - 1)];
+          else if (col < HD + 2 * S) v = sT[(size_t)t * TP + (2 * S - 1) + (tx - (col - HD - S) + S - 1)];
+          else v = __float2half_rn(0.f);
+          hv[j] = v;
+        }
       }
       *reinterpret_cast<uint4*>(Qx + (bh * L + tt) * DK + c8) = *reinterpret_cast<uint4*>(hv);
     }
@@ -170,7 +220,9 @@ attn_prep2_kernel(const __half* __restrict__ qkv, int ldq, const float* __restri
 }
 
 static bool attn_prep2_enabled() {
-  static const int on = [] { const char* e = std::getenv("SAMPT_ATTN_PREP2"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+  // OFF by default: correct (the whole GPU suite passes with it) but measured SLOWER than attn_prep_kernel in the step (748 vs 634 us
+  // per launch, profiles/r02_kernel_table_c2.md): the relative-position products were not what bounds the preparation
+  static const int on = [] { const char* e = std::getenv("SAMPT_ATTN_PREP2"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
   return on != 0;
 }
 
@@ -178,24 +230,37 @@ static bool attn_prep2_enabled() {
 int attn_prep2(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* relh, const float* relw, __half* Qx, __half* Kx,
                __half* Vt, int nwb, int nheads, int S, int Lkp, int DK, int D, int HD, float scale) {
   if (!attn_prep2_enabled()) return 1;
-  if (!(HD == 80 || HD == 64) || DK % 8 != 0 || DK < HD + 2 * S || (DK - HD) % 8 != 0 || Lkp % 8 != 0) return 1;
+  if (!(HD == 80 || HD == 64) || DK % 8 != 0 || DK < HD + 2 * S || (DK - HD) % 8 != 0 || Lkp % 8 != 0 || D % 8 != 0 || ldq % 8 != 0) return 1;
   const int L = S * S;
-  const int TC = (L <= 256) ? ((L + 15) / 16) * 16 : 128;        // a whole 14x14 window (208 rows) or 128 tokens of the global grid
+  if (L > 256) return 1;                                        // windowed blocks only: the 64x64 global grid keeps attn_prep_kernel
+  const int TC = ((L + 15) / 16) * 16;                           // a whole 14x14 window (208 rows)
   const int NRP = ((2 * (2 * S - 1) + 7) / 8) * 8;
   const int QP = HD + 8, TP = NRP + 8;
-  // shared memory: sq + max(sv, sT) + Rcat hi + lo
-  const size_t sv_or_t = std::max((size_t)TC * QP, (size_t)TC * TP);
+  const size_t sv_or_t = (size_t)TC * (size_t)std::max(QP, TP);
   const size_t smem = ((size_t)TC * QP + sv_or_t + 2 * (size_t)NRP * QP) * sizeof(__half);
-  if (smem > 200 * 1024) return 1;
+  if (smem > 110 * 1024) return 1;                               // two CTAs per SM
+  // the fp16 hi | lo table, library-owned (grows on demand)
+  const size_t tab_bytes = 2 * (size_t)NRP * QP * sizeof(__half);
+  auto it = c->owned.find("attn_prep2:table");
+  if (it == c->owned.end() || it->second.second < tab_bytes) {
+    if (it != c->owned.end()) { SAMPT_CUDA(cudaDeviceSynchronize()); cudaFree(it->second.first); }
+    void* buf = nullptr;
+    SAMPT_CUDA(cudaMalloc(&buf, tab_bytes));
+    c->owned["attn_prep2:table"] = {buf, tab_bytes};
+    it = c->owned.find("attn_prep2:table");
+  }
+  __half* tab = reinterpret_cast<__half*>(it->second.first);
   dim3 grid(cdiv(L, TC), nheads, nwb);
   if (HD == 80) {
-    SAMPT_TRY(ensure_func_smem(c, "attn_prep2_kernel<80>", attn_prep2_kernel<80>, 200 * 1024));
-    attn_prep2_kernel<80><<<grid, 256, smem, st>>>(qkv, ldq, relh, relw, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC, NRP);
+    relpos_table_kernel<80><<<cdiv(NRP * QP, 256), 256, 0, st>>>(relh, relw, tab, S, NRP);
+    SAMPT_TRY(ensure_func_smem(c, "attn_prep2_kernel<80>", attn_prep2_kernel<80>, 110 * 1024));
+    attn_prep2_kernel<80><<<grid, 256, smem, st>>>(qkv, ldq, tab, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC, NRP);
   } else {
-    SAMPT_TRY(ensure_func_smem(c, "attn_prep2_kernel<64>", attn_prep2_kernel<64>, 200 * 1024));
-    attn_prep2_kernel<64><<<grid, 256, smem, st>>>(qkv, ldq, relh, relw, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC, NRP);
+    relpos_table_kernel<64><<<cdiv(NRP * QP, 256), 256, 0, st>>>(relh, relw, tab, S, NRP);
+    SAMPT_TRY(ensure_func_smem(c, "attn_prep2_kernel<64>", attn_prep2_kernel<64>, 110 * 1024));
+    attn_prep2_kernel<64><<<grid, 256, smem, st>>>(qkv, ldq, tab, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC, NRP);
   }
-  c->launches++;
+  c->launches += 2;
   SAMPT_LAUNCH_CHECK();
   return 0;
 }

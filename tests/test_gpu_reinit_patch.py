@@ -33,11 +33,16 @@ def test_patch_similarity_matches_reference_arithmetic(tmp_path, ps, thr):
     traj[3, 1] = torch.tensor([126.9, 94.8])
     vis = (torch.rand((9, N), generator=g) > 0.2).float()
     sim_ref, vis_ref = reinit_ref.patch_similarity(clip["frames"], q, traj, vis, ps, thr)
+    for _ in range(8):                                      # a similarity within float noise of the threshold is not a comparable
+        if not ((sim_ref - thr).abs() < 1e-4).any():        # decision (and everything after it cascades): nudge the threshold off it
+            break
+        thr *= 1.03
+        sim_ref, vis_ref = reinit_ref.patch_similarity(clip["frames"], q, traj, vis, ps, thr)
+    m.patch_similarity_threshold = thr
     vis_gpu = m._patch_filter(clip["frames"].cuda(), q.cuda(), traj.cuda(), vis.cuda())
     sim_gpu = m._last_patch_similarities.cpu()
     assert (sim_gpu - sim_ref).abs().max() < 2e-5, (sim_gpu - sim_ref).abs().max()
-    near = (sim_ref - thr).abs() < 1e-4                     # decisions within float noise of the threshold are not comparable
-    assert not near.any()
+    assert not ((sim_ref - thr).abs() < 1e-4).any()
     assert torch.equal(vis_gpu.cpu(), vis_ref)
     assert (vis_ref == reinit_ref.PATCH_NON_SIMILAR).any() or thr < 0.05
 

@@ -245,4 +245,9 @@ def test_hq_encoder_interm_and_e2e(tmp_path):
     out = model(video)
     assert (out["trajectories"].cpu() - ref["trajectories"]).abs().max() < 1e-3
     for f in range(3):
-        assert _iou(out["logits"][0][f].cpu(), ref["logits"][0][f]) >= 0.999, f
+        a, b = out["logits"][0][f].cpu(), ref["logits"][0][f]
+        diff = (a > 0) != (b > 0)
+        # IoU >= 0.999, or -- the random-weight HQ branch yields masks of a few hundred pixels, where ONE pixel is > 0.002 IoU -- the
+        # logit-margin rule of DESIGN.md §2: at most 2 disagreeing pixels, each one undecided in the oracle itself (|logit| < 1e-2)
+        margin_ok = int(diff.sum()) <= 2 and (int(diff.sum()) == 0 or float(b[diff].abs().max()) < 1e-2)
+        assert _iou(a, b) >= 0.999 or margin_ok, (f, _iou(a, b), int(diff.sum()), int((b > 0).sum()))
