@@ -97,6 +97,18 @@ int sampt_gemm_f16(sampt_ctx* ctx, const void* A, int lda, const void* B, int ld
                    int is_bf16, const float* bias, int act, void* out16, float* out32, const float* resid, int ldc,
                    int split_off, void* stream);
 
+/* The same product with the two CORRECTION passes in e4m3 (tcgen05.mma.kind::f8f6f4, twice the fp16 rate): the terms
+ * A_lo.B_hi and A_hi.B_lo are 2^-12 of the result, so e4m3's 2^-5 rounding leaves a 2^-17 residual -- fp32-like products
+ * for 2 fp16-pass equivalents instead of 3.  Rows of 2K fp16 units:
+ *   A: [fp16(x) : K halves | e4m3((x - fp16(x)) * 2^12) : K bytes | e4m3(x * 2^-3) : K bytes]        (sampt_split_f8c)
+ *   B: [fp16(w * 2^s) : K halves | e4m3(w * 2^(s-12)) : K bytes | e4m3((w * 2^s - fp16(w * 2^s)) * 2^3) : K bytes]
+ * with s the largest exponent keeping |w| * 2^s <= 2^15; acc_scale_dev points to 2^-s.  out_f8 != 0 with split_off = N: the
+ * output is written in the A layout of the next such GEMM.  Needs M >= 256, N % 256 == 0, K % 128 == 0 (CTA-pair kernel).
+ * Same role as sampt_gemm_f16 (torch.nn.Linear of the un-vendored image_encoder; call site sam_pt/modeling/sam_pt.py:849). */
+int sampt_gemm_f8c(sampt_ctx* ctx, const void* A, const void* B, int M, int N, int K, const float* acc_scale_dev, const float* bias,
+                   int act, void* out16, float* out32, const float* resid, int ldc, int split_off, int out_f8, void* stream);
+int sampt_split_f8c(sampt_ctx* ctx, const float* x, int M, int K, void* out, void* stream);
+
 /* softmax(Qx Kx^T) V on tcgen05 with pre-extended operands (rel-pos folded into the contraction, see csrc/attn_tc.cu):
  * Qx [BH,Lq,DK], Kx [BH,Lk,DK], Vt [BH,HD,Lkp] fp16; out fp16 [(BH/nheads)*Lq, ld_out] with head h at columns h*HD.
  * Replaces Attention.forward + add_decomposed_rel_pos of upstream image_encoder.py. */
@@ -112,7 +124,9 @@ int sampt_pil_resize_u8(sampt_ctx* ctx, const uint8_t* in, int B, int H, int W, 
 /* Sam.preprocess + ImageEncoderViT.forward for a batch of resized uint8 frames (B,3,Hr,Wr) -> features (B,C,g,g) fp32
  * [+ interm (B,g,g,D): output of the first global-attention block, HQ-SAM].  global_idx / pixel_mean / pixel_std are
  * HOST arrays.  precision: 1/2 as in sampt_gemm_f16 for every GEMM; 3 = 3 split passes for the MLP / patch-embed / neck GEMMs
- * and 2 (weights split) for qkv / proj, whose activations are fp16-limited by the attention path; 4 = 3 passes everywhere.  Replaces SamPredictor.set_image's encoder call (sam_pt.py:849). */
+ * and 2 (weights split) for qkv / proj, whose activations are fp16-limited by the attention path; 4 = 3 passes everywhere;
+ * 5 = 3 passes except qkv (2); 6 = like 4 with the correction passes of qkv / lin1 / lin2 in e4m3 (sampt_gemm_f8c; needs the
+ * "<layer>.w8" / ".w8s" tensors registered).  Replaces SamPredictor.set_image's encoder call (sam_pt.py:849). */
 int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B, int Hr, int Wr, int depth, int embed_dim, int num_heads,
                      int window_size, const int* global_idx_host, int n_global, int img_size, int patch_size, int out_chans,
                      int precision, const float* pixel_mean_host, const float* pixel_std_host, float* features, float* interm,

@@ -220,9 +220,9 @@ attn_prep2_kernel(const __half* __restrict__ qkv, int ldq, const __half* __restr
 }
 
 static bool attn_prep2_enabled() {
-  // OFF by default: correct (the whole GPU suite passes with it) but measured SLOWER than attn_prep_kernel in the step (748 vs 634 us
-  // per launch, profiles/r02_kernel_table_c2.md): the relative-position products were not what bounds the preparation
-  static const int on = [] { const char* e = std::getenv("SAMPT_ATTN_PREP2"); return (e != nullptr && e[0] == '1') ? 1 : 0; }();
+  // ON unless SAMPT_ATTN_PREP2=0.  Parity-tested on hardware (encoder, C1, full C2); 436 us per windowed launch in the step against
+  // 634 us for attn_prep_kernel (gpurun_out/kernel_table_prep2b.md); the first version (plain loads, uncoalesced V^T) took 748 us.
+  static const int on = [] { const char* e = std::getenv("SAMPT_ATTN_PREP2"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
   return on != 0;
 }
 

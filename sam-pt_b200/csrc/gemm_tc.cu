@@ -210,7 +210,12 @@ int gemm_tc(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int 
   SAMPT_CHECK(seg.nseg >= 1 && seg.nseg <= 3, "gemm_tc: nseg out of range");
   SAMPT_CHECK((ep.out16 != nullptr) != (ep.out32 != nullptr), "gemm_tc: exactly one of out16/out32 must be set");
   SAMPT_CHECK(ep.ldc % 8 == 0, "gemm_tc: ldc must be a multiple of 8");
-  if (gemm_tc2_applicable(M, N, K, ep)) return gemm_tc2(c, st, A, lda, B, ldb, M, N, K, seg, ep);
+  if (gemm_tc2_applicable(M, N, K, ep)) {
+    SAMPT_CHECK(!(seg.f8[0] | seg.f8[1] | seg.f8[2]) || K % 128 == 0, "gemm_tc: e4m3 segments need K %% 128 == 0 (K = %d)", K);
+    return gemm_tc2(c, st, A, lda, B, ldb, M, N, K, seg, ep);
+  }
+  SAMPT_CHECK(!(seg.f8[0] | seg.f8[1] | seg.f8[2]) && !ep.out_f8 && ep.acc_scale == nullptr,
+              "gemm_tc: the fp8-corrected GEMM runs on the CTA-pair kernel only (M >= 256, N %% 256 == 0, K %% 128 == 0)");
   SAMPT_TRY(ensure_func_smem(c, "gemm_tc_kernel", gemm_tc_kernel, G_SMEM_BYTES));
   CUtensorMap tmA, tmB;
   // the A/B matrices may carry several K segments side by side (hi | lo): inner extent = lda / ldb
@@ -257,4 +262,31 @@ extern "C" int sampt_gemm_f16(sampt_ctx* ctx, const void* A, int lda, const void
   ep.split_off = split_off;
   ep.is_bf16 = is_bf16;
   return gemm_tc(c, reinterpret_cast<cudaStream_t>(stream), A, lda, B, ldb, M, N, K, seg, ep);
+}
+
+// fp8-corrected split GEMM (tc_api.cuh, "precision 6"): C = act((A_hi.B_hi + A_lo8.B_hi8 + A_hi8.B_lo8) * acc_scale + bias).
+// A [M, 2K] and B [N, 2K] fp16 units in the layouts of tc_api.cuh (sampt_split_f8c builds A; the host builds B once per weight).
+extern "C" int sampt_gemm_f8c(sampt_ctx* ctx, const void* A, const void* B, int M, int N, int K, const float* acc_scale_dev,
+                              const float* bias, int act, void* out16, float* out32, const float* resid, int ldc, int split_off,
+                              int out_f8, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  SAMPT_CHECK(gemm_f8c_applicable(M, N, K), "sampt_gemm_f8c: needs M >= 256, N %% 256 == 0, K %% 128 == 0 (got %d x %d x %d)", M, N, K);
+  GemmEpi ep{};
+  ep.out16 = reinterpret_cast<__half*>(out16);
+  ep.out32 = out32;
+  ep.resid = resid;
+  ep.bias = bias;
+  ep.ldc = ldc;
+  ep.act = act;
+  ep.split_off = split_off;
+  ep.out_f8 = out_f8;
+  ep.acc_scale = acc_scale_dev;
+  return gemm_tc(c, reinterpret_cast<cudaStream_t>(stream), A, 2 * K, B, 2 * K, M, N, K, make_seg_f8(K), ep);
+}
+
+// x [M, K] fp32 -> the A operand of sampt_gemm_f8c: [fp16(x) | e4m3((x - fp16(x)) * 2^12) | e4m3(x * 2^-3)], 2K fp16 units per row
+extern "C" int sampt_split_f8c(sampt_ctx* ctx, const float* x, int M, int K, void* out, void* stream) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  return ln_rows(c, reinterpret_cast<cudaStream_t>(stream), x, K, nullptr, nullptr, nullptr, 0.f, reinterpret_cast<__half*>(out), 2 * K, K,
+                 M, K, 0, 1);
 }

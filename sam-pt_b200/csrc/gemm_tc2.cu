@@ -71,6 +71,18 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// same tile shape with e4m3 operands: K = 32 per instruction (the same 32 bytes per row), twice the fp16 rate; the instruction
+// descriptor is bit-identical (format code 0 = F16 for kind::f16, E4M3 for kind::f8f6f4)
+__device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
 // arrive on the barrier at this shared-memory offset in BOTH CTAs once all previously issued MMAs have completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
@@ -100,8 +112,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int m_tiles = (M + 2 * P_BM - 1) / (2 * P_BM), n_tiles = N / P_BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int kb_per_seg = K / P_BK;
-  const int num_kb = kb_per_seg * seg.nseg;
+  // k-blocks of 128 bytes per operand row: 64 fp16 or 128 e4m3 elements
+  int seg_kb[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) seg_kb[i] = i < seg.nseg ? (seg.f8[i] ? K / (2 * P_BK) : K / P_BK) : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -129,16 +143,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % P_STAGES;
-          const uint32_t ph = (it / P_STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          const int sg = kb / kb_per_seg, kk = (kb % kb_per_seg) * P_BK;
-          uint8_t* sa = smem + s * P_STAGE_BYTES;
-          uint8_t* sb = sa + P_A_BYTES;
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * P_STAGE_BYTES);   // bytes of both CTAs land on the leader's barrier
-          tma_load_2d_pair(sa, &tmA, &full_bar[s], seg.a_off[sg] + kk, m_blk * 2 * P_BM + (int)rank * P_BM);
-          tma_load_2d_pair(sb, &tmB, &full_bar[s], seg.b_off[sg] + kk, n_blk * P_BN + (int)rank * (P_BN / 2));
+        for (int sg = 0; sg < seg.nseg; ++sg) {
+          for (int kb = 0; kb < seg_kb[sg]; ++kb, ++it) {
+            const int s = it % P_STAGES;
+            const uint32_t ph = (it / P_STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const int kk = kb * P_BK;   // in fp16 units of the tensor map (an e4m3 block is the same 128 bytes)
+            uint8_t* sa = smem + s * P_STAGE_BYTES;
+            uint8_t* sb = sa + P_A_BYTES;
+            if (leader) mbar_expect_tx(&full_bar[s], 2 * P_STAGE_BYTES);   // bytes of both CTAs land on the leader's barrier
+            tma_load_2d_pair(sa, &tmA, &full_bar[s], seg.a_off[sg] + kk, m_blk * 2 * P_BM + (int)rank * P_BM);
+            tma_load_2d_pair(sb, &tmB, &full_bar[s], seg.b_off[sg] + kk, n_blk * P_BN + (int)rank * (P_BN / 2));
+          }
         }
       }
     }
@@ -153,18 +169,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&tempty_bar[acc], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P_BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % P_STAGES;
-          const uint32_t ph = (it / P_STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * P_STAGE_BYTES);
-          const uint64_t adesc = make_smem_desc_sw128(sa);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + P_A_BYTES);
+        uint32_t first = 0;   // 0 until the first MMA of the tile has been issued (it overwrites the accumulator)
+        for (int sg = 0; sg < seg.nseg; ++sg) {
+          const bool f8 = seg.f8[sg] != 0;
+          for (int kb = 0; kb < seg_kb[sg]; ++kb, ++it) {
+            const int s = it % P_STAGES;
+            const uint32_t ph = (it / P_STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * P_STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc_sw128(sa);
+            const uint64_t bdesc = make_smem_desc_sw128(sa + P_A_BYTES);
+            if (f8) {
 #pragma unroll
-          for (int k = 0; k < P_BK / 16; ++k)
-            umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          umma_commit_pair(&empty_bar[s]);
+              for (int k = 0; k < P_BK / 16; ++k) {   // 4 x K=32 bytes
+                umma_f8_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first);
+                first = 1;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < P_BK / 16; ++k) {   // 4 x K=16 halves
+                umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first);
+                first = 1;
+              }
+            }
+            umma_commit_pair(&empty_bar[s]);
+          }
         }
         umma_commit_pair(&tfull_bar[acc]);
       }
@@ -184,6 +214,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       long long drow = m;
       if (ep.rowmap && row_ok) drow = ep.rowmap[m];
       const bool store_ok = row_ok && drow >= 0;
+      const float acc_scale = ep.acc_scale ? __ldg(ep.acc_scale) : 1.0f;
 #pragma unroll 1
       for (int ch = 0; ch < P_BN / 32; ++ch) {
         uint32_t r[32];
@@ -193,7 +224,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int n0 = n_blk * P_BN + ch * 32;
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * acc_scale;
         if (ep.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + n0 + j);
@@ -236,7 +267,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
 #pragma unroll
           for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
-          if (ep.split_off > 0) {
+          if (ep.split_off > 0 && ep.out_f8) {
+            // fp8 correction operands of the next GEMM (tc_api.cuh): remainder * 2^12 and value * 2^-3 as e4m3 bytes
+            uint8_t* ob = reinterpret_cast<uint8_t*>(ep.out16 + (size_t)drow * ep.ldc + ep.split_off) + n0;
+            uint32_t l8[8], h8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __half2 ha = *reinterpret_cast<__half2*>(&hi[2 * j]), hb = *reinterpret_cast<__half2*>(&hi[2 * j + 1]);
+              const float2 fa = __half22float2(ha), fb = __half22float2(hb);
+              l8[j] = cvt_e4m3x4((v[4 * j] - fa.x) * F8_LO_SCALE, (v[4 * j + 1] - fa.y) * F8_LO_SCALE,
+                                 (v[4 * j + 2] - fb.x) * F8_LO_SCALE, (v[4 * j + 3] - fb.y) * F8_LO_SCALE);
+              h8[j] = cvt_e4m3x4(v[4 * j] * F8_HI_SCALE, v[4 * j + 1] * F8_HI_SCALE, v[4 * j + 2] * F8_HI_SCALE, v[4 * j + 3] * F8_HI_SCALE);
+            }
+            *reinterpret_cast<uint4*>(ob) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+            *reinterpret_cast<uint4*>(ob + 16) = make_uint4(l8[4], l8[5], l8[6], l8[7]);
+            *reinterpret_cast<uint4*>(ob + ep.split_off) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+            *reinterpret_cast<uint4*>(ob + ep.split_off + 16) = make_uint4(h8[4], h8[5], h8[6], h8[7]);
+          } else if (ep.split_off > 0) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
               *reinterpret_cast<uint4*>(o + ep.split_off + 2 * j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
@@ -261,6 +308,11 @@ bool gemm_tc2_applicable(int M, int N, int K, const GemmEpi& ep) {
   static const int enabled = [] { const char* e = std::getenv("SAMPT_GEMM_2CTA"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();   // validated on hardware in round 2: on unless =0
   (void)ep;
   return enabled && N % P_BN == 0 && K % P_BK == 0 && M >= 2 * P_BM;
+}
+// the fp8-corrected segments additionally need whole 128-element k-blocks
+bool gemm_f8c_applicable(int M, int N, int K) {
+  GemmEpi ep{};
+  return gemm_tc2_applicable(M, N, K, ep) && K % (2 * P_BK) == 0;
 }
 
 int gemm_tc2(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmSeg& seg,

@@ -63,7 +63,7 @@ int preprocess_im2col(Ctx* c, cudaStream_t st, const uint8_t* img, __half* A, in
                       int split_off, const float* mean, const float* stdv);
 int im2col_f32(Ctx* c, cudaStream_t st, const float* img, __half* A, int B, int G, int P, int ld, int split_off);
 int ln_rows(Ctx* c, cudaStream_t st, const float* x, int ldx, const int* src, const float* gamma, const float* beta, float eps,
-            __half* out, int ldo, int split_off, int Mout, int D, int normalize);
+            __half* out, int ldo, int split_off, int Mout, int D, int normalize, int f8 = 0);
 int attn_prep(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* relh, const float* relw, __half* Qx, __half* Kx,
               __half* Vt, int nwb, int nheads, int S, int Lkp, int DK, int D, int HD, float scale);
 int attn_prep2(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float* relh, const float* relw, __half* Qx, __half* Kx,

@@ -156,6 +156,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// four floats -> four e4m3 bytes (round to nearest, saturating), element 0 in the lowest byte
+__device__ __forceinline__ uint32_t cvt_e4m3x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));   // first source -> upper byte
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+
 // ------------------------------------------------------------------ descriptors
 // K-major operand tile in shared memory, 128-byte swizzle (rows of 64 halves = 128 B, 8-row groups of 1024 B):
 //   start>>4 [0,14) | LBO>>4 [16,30) = 1 (unused for swizzled K-major) | SBO>>4 [32,46) = 64 (1024 B) |

@@ -4,6 +4,8 @@
 // Upstream arithmetic: segment_anything/modeling/image_encoder.py (un-vendored).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_common.cuh"
+#include "tc_api.cuh"
 
 namespace sampt {
 
@@ -122,7 +124,7 @@ int preprocess_im2col(Ctx* c, cudaStream_t st, const uint8_t* img, __half* A, in
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ src, const float* __restrict__ gamma,
                const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo, int split_off, int Mout, int D,
-               int normalize) {
+               int normalize, int f8) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= Mout) return;
@@ -133,7 +135,7 @@ ln_rows_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ src
     for (int i = 0; i < nv; ++i) {
       int col = (i * 32 + lane) * 4;
       *reinterpret_cast<uint2*>(o + col) = make_uint2(0u, 0u);
-      if (split_off > 0) *reinterpret_cast<uint2*>(o + split_off + col) = make_uint2(0u, 0u);
+      if (split_off > 0) *reinterpret_cast<uint2*>(o + split_off + col) = make_uint2(0u, 0u);   // (f8: the same 2*D bytes, zero = 0.0 in e4m3)
     }
     return;
   }
@@ -175,7 +177,15 @@ ln_rows_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ src
       }
       __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
       *reinterpret_cast<uint2*>(o + col) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-      if (split_off > 0) {
+      if (split_off > 0 && f8) {
+        // fp8 correction operands (tc_api.cuh): e4m3(remainder * 2^12) | e4m3(value * 2^-3), D bytes each behind the hi block
+        float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        uint8_t* ob = reinterpret_cast<uint8_t*>(o + split_off) + col;
+        *reinterpret_cast<uint32_t*>(ob) = tc::cvt_e4m3x4((r[0] - f0.x) * F8_LO_SCALE, (r[1] - f0.y) * F8_LO_SCALE,
+                                                          (r[2] - f1.x) * F8_LO_SCALE, (r[3] - f1.y) * F8_LO_SCALE);
+        *reinterpret_cast<uint32_t*>(ob + split_off) =
+            tc::cvt_e4m3x4(r[0] * F8_HI_SCALE, r[1] * F8_HI_SCALE, r[2] * F8_HI_SCALE, r[3] * F8_HI_SCALE);
+      } else if (split_off > 0) {
         float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
         __half2 l0 = __floats2half2_rn(r[0] - f0.x, r[1] - f0.y), l1 = __floats2half2_rn(r[2] - f1.x, r[3] - f1.y);
         *reinterpret_cast<uint2*>(o + split_off + col) =
@@ -185,9 +195,10 @@ ln_rows_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ src
   }
 }
 int ln_rows(Ctx* c, cudaStream_t st, const float* x, int ldx, const int* src, const float* gamma, const float* beta, float eps,
-            __half* out, int ldo, int split_off, int Mout, int D, int normalize) {
+            __half* out, int ldo, int split_off, int Mout, int D, int normalize, int f8) {
   SAMPT_CHECK(D % 128 == 0 && D <= 1536, "ln_rows: D=%d must be a multiple of 128 and <= 1536", D);
-  ln_rows_kernel<<<cdiv(Mout, 8), 256, 0, st>>>(x, ldx, src, gamma, beta, eps, out, ldo, split_off, Mout, D, normalize);
+  SAMPT_CHECK(!f8 || split_off == D, "ln_rows: the fp8 layout puts the byte blocks right behind the D hi halves");
+  ln_rows_kernel<<<cdiv(Mout, 8), 256, 0, st>>>(x, ldx, src, gamma, beta, eps, out, ldo, split_off, Mout, D, normalize, f8);
   c->launches++;
   SAMPT_LAUNCH_CHECK();
   return 0;

@@ -111,6 +111,10 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
   // precision 5: like 3, but the attention OUTPUT is carried as fp16 hi|lo and the proj GEMM runs all three passes -- the
   // attention kernel accumulates O in fp32, so this removes the 2^-11 rounding of proj's input; qkv stays at two passes (its
   // output is rounded to fp16 for the attention operands whatever the GEMM does).
+  // precision 6: like 4 (every product to ~2^-22), but the two CORRECTION passes of the qkv / lin1 / lin2 GEMMs run in e4m3 on
+  // tcgen05.mma.kind::f8f6f4 at twice the fp16 rate: A_lo.B_hi and A_hi.B_lo are 2^-12 of the result, so the 2^-5 relative
+  // rounding of their fp8 operands leaves a 2^-17 residual (tc_api.cuh: make_seg_f8).  2 fp16-pass equivalents instead of 3.
+  const bool f8c = precision == 6;
   const int p_qkv = (precision == 3 || precision == 5) ? 2 : (precision >= 4 ? 3 : precision);
   const int p_proj = precision == 3 ? 2 : (precision >= 4 ? 3 : precision);
   if (precision >= 4) precision = 3;
@@ -161,7 +165,7 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
   bool save_const = false;    // this call runs in full and saves the constant rows before block fg
   if (pad_candidate) {
     char key[160];
-    snprintf(key, sizeof(key), "vitconst:%dx%d:g%d:w%d:d%d:D%d:fg%d:p%d", Hr, Wr, G, ws, d.depth, D, fg, precision * 100 + p_qkv * 10 + p_proj);
+    snprintf(key, sizeof(key), "vitconst:%dx%d:g%d:w%d:d%d:D%d:fg%d:p%d", Hr, Wr, G, ws, d.depth, D, fg, precision * 100 + p_qkv * 10 + p_proj + (f8c ? 1000 : 0));
     auto it = c->owned.find(key);
     if (it == c->owned.end()) {
       void* buf = nullptr;
@@ -213,6 +217,14 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
     SAMPT_TRY(get_f32(c, bp + "attn.rel_pos_h", &rph)); SAMPT_TRY(get_f32(c, bp + "attn.rel_pos_w", &rpw));
     SAMPT_TRY(get_f16(c, bp + "attn.qkv.w16", &wqkv)); SAMPT_TRY(get_f16(c, bp + "attn.proj.w16", &wproj));
     SAMPT_TRY(get_f16(c, bp + "mlp.lin1.w16", &wl1)); SAMPT_TRY(get_f16(c, bp + "mlp.lin2.w16", &wl2));
+    // fp8-corrected operands of the three large GEMMs (registered by the host next to the hi|lo copies when precision == 6)
+    const __half *w8qkv = nullptr, *w8l1 = nullptr, *w8l2 = nullptr;
+    const float *s8qkv = nullptr, *s8l1 = nullptr, *s8l2 = nullptr;
+    if (f8c) {
+      SAMPT_TRY(get_f16(c, bp + "attn.qkv.w8", &w8qkv)); SAMPT_TRY(get_f32(c, bp + "attn.qkv.w8s", &s8qkv));
+      SAMPT_TRY(get_f16(c, bp + "mlp.lin1.w8", &w8l1)); SAMPT_TRY(get_f32(c, bp + "mlp.lin1.w8s", &s8l1));
+      SAMPT_TRY(get_f16(c, bp + "mlp.lin2.w8", &w8l2)); SAMPT_TRY(get_f32(c, bp + "mlp.lin2.w8s", &s8l2));
+    }
 
     if (blk == fg && pad_candidate) {
       const int D4 = D / 4;
@@ -237,13 +249,23 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
     const int DK = is_global ? DKg : DKw;
     const int Lkp = is_global ? GG : Lkpw;
     const int NT = is_global ? 128 : (((Lw + 15) / 16) * 16 <= 256 ? ((Lw + 15) / 16) * 16 : 128);
+    // which GEMMs of this block take the fp8-corrected form (shape gate of the CTA-pair kernel; else three fp16 passes)
+    const bool f8_qkv = f8c && gemm_f8c_applicable(Mrows, 3 * D, D);
+    const bool f8_l1 = f8c && gemm_f8c_applicable(Mmlp, 4 * D, D);
+    const bool f8_l2 = f8c && gemm_f8c_applicable(Mmlp, D, 4 * D);
     // LN1 (+ window partition with zero padding)
-    SAMPT_TRY(ln_rows(c, st, x, D, is_global ? nullptr : blk_wmap, n1w, n1b, 1e-6f, A, D * asp, (asp == 2 && p_qkv == 3) ? D : 0, Mrows, D, 1));
+    SAMPT_TRY(ln_rows(c, st, x, D, is_global ? nullptr : blk_wmap, n1w, n1b, 1e-6f, A, D * asp, (asp == 2 && p_qkv == 3) ? D : 0, Mrows, D, 1,
+                      f8_qkv));
     // qkv = Linear(D, 3D)
     {
       GemmEpi ep{};
       ep.out16 = qkv; ep.bias = qkvb; ep.ldc = 3 * D;
-      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wqkv, D * bsp, Mrows, 3 * D, D, make_seg(p_qkv, D), ep));
+      if (f8_qkv) {
+        ep.acc_scale = s8qkv;
+        SAMPT_TRY(gemm_tc(c, st, A, D * 2, w8qkv, D * 2, Mrows, 3 * D, D, make_seg_f8(D), ep));
+      } else {
+        SAMPT_TRY(gemm_tc(c, st, A, D * asp, wqkv, D * bsp, Mrows, 3 * D, D, make_seg(p_qkv, D), ep));
+      }
     }
     // attention
     SAMPT_TRY(attn_prep(c, st, qkv, 3 * D, rph, rpw, Qx, Kx, Vt, nwb, d.nheads, S, Lkp, DK, D, HD, 1.0f / sqrtf((float)HD)));
@@ -255,16 +277,27 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
       SAMPT_TRY(gemm_tc(c, st, att, D * asp, wproj, D * bsp, Mrows, D, D, make_seg(p_proj, D), ep));
     }
     // x = x + lin2(gelu(lin1(LN2(x))))
-    SAMPT_TRY(ln_rows(c, st, x, D, live_only ? tmap_c : nullptr, n2w, n2b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mmlp, D, 1));
+    SAMPT_TRY(ln_rows(c, st, x, D, live_only ? tmap_c : nullptr, n2w, n2b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mmlp, D, 1, f8_l1));
     {
       GemmEpi ep{};
       ep.out16 = hbuf; ep.bias = l1b; ep.ldc = 4 * D * asp; ep.act = 1; ep.split_off = asp == 2 ? 4 * D : 0;
-      SAMPT_TRY(gemm_tc(c, st, A, D * asp, wl1, D * bsp, Mmlp, 4 * D, D, make_seg(precision, D), ep));
+      ep.out_f8 = f8_l2;   // lin2's A operand in the layout lin2 will read
+      if (f8_l1) {
+        ep.acc_scale = s8l1;
+        SAMPT_TRY(gemm_tc(c, st, A, D * 2, w8l1, D * 2, Mmlp, 4 * D, D, make_seg_f8(D), ep));
+      } else {
+        SAMPT_TRY(gemm_tc(c, st, A, D * asp, wl1, D * bsp, Mmlp, 4 * D, D, make_seg(precision, D), ep));
+      }
     }
     {
       GemmEpi ep{};
       ep.out32 = x; ep.resid = x; ep.bias = l2b; ep.ldc = D; ep.rowmap = live_only ? tmap_c : nullptr;
-      SAMPT_TRY(gemm_tc(c, st, hbuf, 4 * D * asp, wl2, 4 * D * bsp, Mmlp, D, 4 * D, make_seg(precision, 4 * D), ep));
+      if (f8_l2) {
+        ep.acc_scale = s8l2;
+        SAMPT_TRY(gemm_tc(c, st, hbuf, 4 * D * 2, w8l2, 4 * D * 2, Mmlp, D, 4 * D, make_seg_f8(4 * D), ep));
+      } else {
+        SAMPT_TRY(gemm_tc(c, st, hbuf, 4 * D * asp, wl2, 4 * D * bsp, Mmlp, D, 4 * D, make_seg(precision, 4 * D), ep));
+      }
     }
     if (is_global) {
       if (interm && gi == 0)
@@ -309,7 +342,7 @@ extern "C" int sampt_vit_encode(sampt_ctx* ctx, const uint8_t* resized_u8, int B
                                 int patch_size, int out_chans, int precision, const float* pixel_mean_host,
                                 const float* pixel_std_host, float* features, float* interm, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
-  SAMPT_CHECK(precision >= 1 && precision <= 5, "sampt_vit_encode: precision must be 1..5");
+  SAMPT_CHECK(precision >= 1 && precision <= 6, "sampt_vit_encode: precision must be 1..6");
   SAMPT_CHECK(img_size % patch_size == 0, "img_size must be a multiple of patch_size");
   SAMPT_CHECK(Hr <= img_size && Wr <= img_size, "resized image (%dx%d) exceeds img_size %d", Hr, Wr, img_size);
   SAMPT_CHECK(embed_dim % 128 == 0 && embed_dim % num_heads == 0, "embed_dim must be a multiple of 128 and of num_heads");
@@ -323,7 +356,7 @@ extern "C" int sampt_vit_encode_f32(sampt_ctx* ctx, const float* x, int B, int d
                                     const int* global_idx_host, int n_global, int img_size, int patch_size, int out_chans,
                                     int precision, float* features, float* interm, void* stream) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
-  SAMPT_CHECK(precision >= 1 && precision <= 5, "sampt_vit_encode_f32: precision must be 1..5");
+  SAMPT_CHECK(precision >= 1 && precision <= 6, "sampt_vit_encode_f32: precision must be 1..6");
   SAMPT_CHECK(img_size % patch_size == 0, "img_size must be a multiple of patch_size");
   SAMPT_CHECK(embed_dim % 128 == 0 && embed_dim % num_heads == 0, "embed_dim must be a multiple of 128 and of num_heads");
   VitDims d{depth, embed_dim, num_heads, window_size, img_size / patch_size, patch_size, out_chans};

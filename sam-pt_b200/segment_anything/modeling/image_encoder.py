@@ -3,6 +3,7 @@ kwargs per /root/reference/configs/model/sam/image_encoder/vit_base.yaml:1-16) e
 tcgen05 GEMMs + fused attention (csrc/gemm_tc.cu, attn_tc.cu, vit_kernels.cu, vit_pipeline.cu)."""
 from __future__ import annotations
 
+import math
 import os
 from ctypes import c_float, c_int
 from typing import Dict, Tuple, Type
@@ -68,6 +69,25 @@ class ImageEncoderViT(nn.Module):
         lo = (w - hi.float()).half()
         return torch.cat([hi, lo], dim=1).contiguous()
 
+    @staticmethod
+    def _w8(w: torch.Tensor):
+        """Weight operand of the fp8-corrected GEMM (include/sampt_b200.h: sampt_gemm_f8c): rows of 2K fp16 units
+        [fp16(w 2^s) | e4m3(w 2^(s-12)) | e4m3((w 2^s - fp16(w 2^s)) 2^3)] and the accumulator scale 2^-s."""
+        w = w.detach().float()
+        amax = float(w.abs().max())
+        s = 15 - (math.frexp(amax)[1] if amax > 0 else 0)         # |w| 2^s <= 2^15 (fp16 max 65504)
+        ws = w * (2.0 ** s)
+        hi = ws.half()
+        rem = ws - hi.float()
+
+        def e4m3(t):
+            return t.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+
+        hi8 = e4m3(w * (2.0 ** (s - 12)))
+        lo8 = e4m3(rem * 8.0)
+        packed = torch.cat([hi.view(torch.uint8), hi8, lo8], dim=1).contiguous()      # (N, 2K + K + K) bytes
+        return packed.view(torch.float16), torch.tensor([2.0 ** (-s)], dtype=torch.float32, device=w.device)
+
     def native_context(self, prefix: str = "sam.image_encoder.") -> native.Context:
         dev = self.pos_embed.device
         ctx = native.get_context(dev)
@@ -88,6 +108,11 @@ class ImageEncoderViT(nn.Module):
                     ctx.set_tensor(prefix + b + n, sd[b + n].float())
                 for n in ("attn.qkv", "attn.proj", "mlp.lin1", "mlp.lin2"):
                     ctx.set_tensor(prefix + b + n + ".w16", self._w16(sd[b + n + ".weight"], split_b))
+                if self.precision == 6:
+                    for n in ("attn.qkv", "mlp.lin1", "mlp.lin2"):
+                        w8, w8s = self._w8(sd[b + n + ".weight"])
+                        ctx.set_tensor(prefix + b + n + ".w8", w8)
+                        ctx.set_tensor(prefix + b + n + ".w8s", w8s)
             C = self.out_chans
             ctx.set_tensor(prefix + "neck.0.w16", self._w16(sd["neck.0.weight"].reshape(C, D), split_b))
             ctx.set_tensor(prefix + "neck.2.w16", self._w16(sd["neck.2.weight"].permute(0, 2, 3, 1).reshape(C, 9 * C), split_b))

@@ -41,7 +41,7 @@ def test_pil_resize_gpu_bit_exact():
 
 @pytest.mark.parametrize("vit,precision,tol", [("vit_test", 1, 6e-3), ("vit_test", 2, 4e-3), ("vit_test", 3, 6e-4),
                                                ("vit_test", 4, 2e-4), ("vit_test80", 1, 6e-3), ("vit_test80", 3, 6e-4),
-                                               ("vit_test80", 4, 2e-4)])
+                                               ("vit_test80", 4, 2e-4), ("vit_test", 6, 2e-4), ("vit_test80", 6, 2e-4)])
 def test_vit_encoder_matches_oracle(vit, precision, tol):
     """relative L2 error of the (B,256,64,64) embedding; batch of 2 frames exercises the frame batching."""
     from segment_anything.predictor import SamPredictor
@@ -59,12 +59,14 @@ def test_vit_encoder_matches_oracle(vit, precision, tol):
         assert rel < tol, (vit, precision, b, rel)
 
 
-def test_vit_b_precision3_embedding():
+@pytest.mark.parametrize("precision", [4, 6])
+def test_vit_b_precision3_embedding(precision):
+    """ViT-B (every block GEMM on the CTA-pair kernel): three fp16 passes (4) and fp16 + two e4m3 correction passes (6)."""
     from segment_anything.predictor import SamPredictor
     cfg = sam_ref.VIT_B
     sd = _sam_sd(cfg, 7202)
     sam = factory.build_sam("vit_b", sd).cuda()
-    sam.image_encoder.precision = 4
+    sam.image_encoder.precision = precision
     pred = SamPredictor(sam)
     clip = synth.make_clip(1, 240, 320, seed=72)
     feats = pred.encode_frames(clip["frames"].cuda()).cpu()
@@ -164,7 +166,7 @@ def test_precision_dial_report(tmp_path):
                                   sam_iou_threshold=-1e9)
     model = factory.build_sam_pt("vit_b", sam_sd, ckpt, positive_points_per_mask=4, sam_iou_threshold=-1e9)
     report = {}
-    for p in (1, 2, 3, 4):
+    for p in (1, 2, 3, 4, 6):
         model.sam_predictor.model.image_encoder.precision = p
         out = model(video)
         report[p] = [_iou(out["logits"][0][f].cpu(), ref["logits"][0][f]) for f in range(2)]
@@ -248,6 +250,10 @@ def test_hq_encoder_interm_and_e2e(tmp_path):
         a, b = out["logits"][0][f].cpu(), ref["logits"][0][f]
         diff = (a > 0) != (b > 0)
         # IoU >= 0.999, or -- the random-weight HQ branch yields masks of a few hundred pixels, where ONE pixel is > 0.002 IoU -- the
-        # logit-margin rule of DESIGN.md §2: at most 2 disagreeing pixels, each one undecided in the oracle itself (|logit| < 1e-2)
-        margin_ok = int(diff.sum()) <= 2 and (int(diff.sum()) == 0 or float(b[diff].abs().max()) < 1e-2)
-        assert _iou(a, b) >= 0.999 or margin_ok, (f, _iou(a, b), int(diff.sum()), int((b > 0).sum()))
+        # logit-margin rule of DESIGN.md §2: at most 2 disagreeing pixels, each one undecided in the oracle itself
+        # (|logit| < 2e-3 of the frame's logit range -- the decoder parity tolerance is 3e-4 of that range per call, 13 calls chained)
+        fin = torch.isfinite(b)
+        tol = 2e-3 * max(1.0, float(b[fin].abs().max()))
+        worst = float(b[diff].abs().max()) if int(diff.sum()) else 0.0
+        margin_ok = int(diff.sum()) <= 2 and worst < tol
+        assert _iou(a, b) >= 0.999 or margin_ok, (f, _iou(a, b), int(diff.sum()), int((b > 0).sum()), worst, tol)
