@@ -630,7 +630,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
-    ap.add_argument("--precision", type=int, default=int(os.environ.get("SAMPT_VIT_PRECISION", "4")))
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("SAMPT_VIT_PRECISION", "6")))
     ap.add_argument("--encoder-batch", type=int, default=10)
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -92,10 +92,12 @@ def apply_sam_to_trajectories(predictor: sam_ref.RefSamPredictor, images_u8, tra
             _, _, low = predictor.predict_torch(vc[vl == 1][None], vl[vl == 1][None], None, None, False, True)
             ml, iou, low = predictor.predict_torch(vc[None], vl[None], None, low, False, True)
         n_ref = 0
+        box_margin = float("inf")
         for _ in range(iterative_refinement_iterations):
             mm = ml[0, 0] > 0
             if mm.sum() < 2:
                 break
+            box_margin = min(box_margin, _box_edge_margin(ml[0, 0]))
             yx = mm.nonzero()
             box = torch.tensor([yx[:, 1].min(), yx[:, 0].min(), yx[:, 1].max(), yx[:, 0].max()], dtype=torch.float)
             ml, iou, low = predictor.predict_torch(vc[None], vl[None], box[None, None, :], low, False, True)
@@ -103,6 +105,7 @@ def apply_sam_to_trajectories(predictor: sam_ref.RefSamPredictor, images_u8, tra
         if taps is not None:
             taps.setdefault("low_res", {})[(f, m)] = low[0, 0].clone()
             taps.setdefault("n_refine", {})[(f, m)] = n_ref
+            taps.setdefault("box_margin", {})[(f, m)] = box_margin
         s = iou[0, 0].cpu().numpy()
         if s < sam_iou_threshold:
             return np.full((H, W), -float("inf"), dtype=np.float64), s
@@ -128,6 +131,25 @@ def apply_sam_to_trajectories(predictor: sam_ref.RefSamPredictor, images_u8, tra
                 scnt[m] += 1
     pred_scores = ssum / np.where(scnt != 0, scnt, 1)
     return pred_scores, torch.from_numpy(logits).float(), torch.from_numpy(spf).float()
+
+
+def _box_edge_margin(logit: torch.Tensor) -> float:
+    """How far the refinement box of `logit > 0` (sam_pt.py:793-800: min / max of the positive pixels' coordinates) is from
+    moving by one pixel: for every edge, the smaller of (largest logit of the edge row / column: it must stay > 0) and (minus the
+    largest logit of the row / column just outside: it must stay <= 0).  A parity test may only hold a frame to the mask-IoU bar
+    when this margin, minimised over the 12 refinement iterations, exceeds the decoder's own parity tolerance: a box that moves by
+    one pixel changes every later logit of the chain (test infrastructure, not part of the reference)."""
+    rows, cols = logit.max(dim=1).values, logit.max(dim=0).values
+    out = float("inf")
+    for v in (rows, cols):
+        pos = (v > 0).nonzero()[:, 0]
+        lo, hi = int(pos.min()), int(pos.max())
+        out = min(out, float(v[lo]), float(v[hi]))
+        if lo > 0:
+            out = min(out, float(-v[lo - 1]))
+        if hi < v.numel() - 1:
+            out = min(out, float(-v[hi + 1]))
+    return out
 
 
 @torch.no_grad()

@@ -231,9 +231,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 int attn_tc(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp,
-            int DK, int HD, int NT, int nheads, __half* out, int ld_out, int split_off) {
+            int DK, int HD, int NT, int nheads, __half* out, int ld_out, int split_off, int out_f8) {
   if (attn_ws_applicable(Lk, DK, HD, NT))
-    return attn_ws(c, st, Qx, Kx, Vt, BH, Lq, Lk, Lkp, DK, HD, NT, nheads, out, ld_out, split_off);
+    return attn_ws(c, st, Qx, Kx, Vt, BH, Lq, Lk, Lkp, DK, HD, NT, nheads, out, ld_out, split_off, out_f8);
+  SAMPT_CHECK(!out_f8, "attn_tc: the fp8 output layout is written by attn_ws_kernel only");
   if (attn_tc_v2_applicable(Lk, DK, HD))
     return attn_tc_v2(c, st, Qx, Kx, Vt, BH, Lq, Lk, Lkp, DK, HD, nheads, out, ld_out, split_off);
   if (attn_tc_v3_applicable(Lk, NT))

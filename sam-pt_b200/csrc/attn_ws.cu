@@ -43,6 +43,7 @@ struct AttnWsParams {
   int ntiles;        // key tiles per item = ceil(Lk / NT)
   __half* out;       // [BH/nheads * Lq, ld_out]
   int ld_out, split_off;
+  int out_f8;        // with split_off > 0: fp8 correction operands of the proj GEMM (tc_api.cuh) instead of the fp16 remainder
 };
 
 constexpr int WS_THREADS = 320;
@@ -342,7 +343,23 @@ attn_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 lo[i >> 1] = *reinterpret_cast<uint32_t*>(&l);
               }
               *reinterpret_cast<uint4*>(op + d0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              if (p.split_off > 0) *reinterpret_cast<uint4*>(op + p.split_off + d0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              if (p.split_off > 0 && p.out_f8) {
+                // e4m3(remainder * 2^12) | e4m3(value * 2^-3): split_off BYTES each, right behind the split_off hi halves of the row
+                uint8_t* ob = reinterpret_cast<uint8_t*>(p.out + orow * p.ld_out + p.split_off) + (size_t)(bh % p.nheads) * p.HD + d0;
+                uint32_t l8[2], h8[2];
+#pragma unroll
+                for (int i = 0; i < 8; i += 4) {
+                  const float a0 = o[d0 + i] * inv, a1 = o[d0 + i + 1] * inv, a2 = o[d0 + i + 2] * inv, a3 = o[d0 + i + 3] * inv;
+                  const float2 f0 = __half22float2(*reinterpret_cast<__half2*>(&hi[i >> 1]));
+                  const float2 f1 = __half22float2(*reinterpret_cast<__half2*>(&hi[(i >> 1) + 1]));
+                  l8[i >> 2] = cvt_e4m3x4((a0 - f0.x) * F8_LO_SCALE, (a1 - f0.y) * F8_LO_SCALE, (a2 - f1.x) * F8_LO_SCALE, (a3 - f1.y) * F8_LO_SCALE);
+                  h8[i >> 2] = cvt_e4m3x4(a0 * F8_HI_SCALE, a1 * F8_HI_SCALE, a2 * F8_HI_SCALE, a3 * F8_HI_SCALE);
+                }
+                *reinterpret_cast<uint2*>(ob) = make_uint2(l8[0], l8[1]);
+                *reinterpret_cast<uint2*>(ob + p.split_off) = make_uint2(h8[0], h8[1]);
+              } else if (p.split_off > 0) {
+                *reinterpret_cast<uint4*>(op + p.split_off + d0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
             }
           }
         }
@@ -371,7 +388,7 @@ bool attn_ws_applicable(int Lk, int DK, int HD, int NT) {
 }
 
 int attn_ws(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp, int DK,
-            int HD, int NT, int nheads, __half* out, int ld_out, int split_off) {
+            int HD, int NT, int nheads, __half* out, int ld_out, int split_off, int out_f8) {
   SAMPT_CHECK(Lkp % 8 == 0 && Lkp >= Lk, "attn_ws: Lkp=%d must be a multiple of 8 and >= Lk", Lkp);
   CUtensorMap tmQ, tmK, tmV;
   SAMPT_TRY(make_tmap_3d_f16(&tmQ, Qx, DK, Lq, BH, (uint64_t)DK * 2, (uint64_t)Lq * DK * 2, 64, 128, 1));
@@ -382,7 +399,7 @@ int attn_ws(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const _
   p.n_pairs = (Lq + 255) / 256;
   p.n_items = p.n_pairs * BH;
   p.ntiles = (Lk + NT - 1) / NT;
-  p.out = out; p.ld_out = ld_out; p.split_off = split_off;
+  p.out = out; p.ld_out = ld_out; p.split_off = split_off; p.out_f8 = out_f8;
   const size_t smem = attn_ws_smem(NT, DK, HD);
   const int grid = std::min(p.n_items, c->num_sms);
   if (HD <= 64) {

@@ -45,8 +45,9 @@ inline GemmSeg make_seg_f8(int K) {
 int gemm_tc(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmSeg& seg,
             const GemmEpi& ep);
 
+// out_f8 (only where attn_ws_applicable): the output row carries the fp8 correction operands of the proj GEMM instead of the fp16 remainder
 int attn_tc(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp,
-            int DK, int HD, int NT, int nheads, __half* out, int ld_out, int split_off);
+            int DK, int HD, int NT, int nheads, __half* out, int ld_out, int split_off, int out_f8 = 0);
 
 // CTA-pair (cta_group::2) variant of gemm_tc (gemm_tc2.cu); on unless SAMPT_GEMM_2CTA=0
 bool gemm_tc2_applicable(int M, int N, int K, const GemmEpi& ep);
@@ -67,6 +68,6 @@ int attn_tc_v3(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, cons
 // round-2 kernel: two softmax warpgroups, P in tensor memory (TS MMA), persistent (attn_ws.cu); on unless SAMPT_ATTN_WS=0
 bool attn_ws_applicable(int Lk, int DK, int HD, int NT);
 int attn_ws(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp, int DK,
-            int HD, int NT, int nheads, __half* out, int ld_out, int split_off);
+            int HD, int NT, int nheads, __half* out, int ld_out, int split_off, int out_f8 = 0);
 
 }  // namespace sampt

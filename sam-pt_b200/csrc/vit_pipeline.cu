@@ -218,9 +218,10 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
     SAMPT_TRY(get_f16(c, bp + "attn.qkv.w16", &wqkv)); SAMPT_TRY(get_f16(c, bp + "attn.proj.w16", &wproj));
     SAMPT_TRY(get_f16(c, bp + "mlp.lin1.w16", &wl1)); SAMPT_TRY(get_f16(c, bp + "mlp.lin2.w16", &wl2));
     // fp8-corrected operands of the three large GEMMs (registered by the host next to the hi|lo copies when precision == 6)
-    const __half *w8qkv = nullptr, *w8l1 = nullptr, *w8l2 = nullptr;
-    const float *s8qkv = nullptr, *s8l1 = nullptr, *s8l2 = nullptr;
+    const __half *w8qkv = nullptr, *w8proj = nullptr, *w8l1 = nullptr, *w8l2 = nullptr;
+    const float *s8qkv = nullptr, *s8proj = nullptr, *s8l1 = nullptr, *s8l2 = nullptr;
     if (f8c) {
+      SAMPT_TRY(get_f16(c, bp + "attn.proj.w8", &w8proj)); SAMPT_TRY(get_f32(c, bp + "attn.proj.w8s", &s8proj));
       SAMPT_TRY(get_f16(c, bp + "attn.qkv.w8", &w8qkv)); SAMPT_TRY(get_f32(c, bp + "attn.qkv.w8s", &s8qkv));
       SAMPT_TRY(get_f16(c, bp + "mlp.lin1.w8", &w8l1)); SAMPT_TRY(get_f32(c, bp + "mlp.lin1.w8s", &s8l1));
       SAMPT_TRY(get_f16(c, bp + "mlp.lin2.w8", &w8l2)); SAMPT_TRY(get_f32(c, bp + "mlp.lin2.w8s", &s8l2));
@@ -251,6 +252,7 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
     const int NT = is_global ? 128 : (((Lw + 15) / 16) * 16 <= 256 ? ((Lw + 15) / 16) * 16 : 128);
     // which GEMMs of this block take the fp8-corrected form (shape gate of the CTA-pair kernel; else three fp16 passes)
     const bool f8_qkv = f8c && gemm_f8c_applicable(Mrows, 3 * D, D);
+    const bool f8_proj = f8c && gemm_f8c_applicable(Mrows, D, D) && attn_ws_applicable(L, DK, HD, NT);   // (attn_ws writes the layout)
     const bool f8_l1 = f8c && gemm_f8c_applicable(Mmlp, 4 * D, D);
     const bool f8_l2 = f8c && gemm_f8c_applicable(Mmlp, D, 4 * D);
     // LN1 (+ window partition with zero padding)
@@ -269,12 +271,18 @@ static int vit_forward(Ctx* c, cudaStream_t st, const uint8_t* img, const float*
     }
     // attention
     SAMPT_TRY(attn_prep(c, st, qkv, 3 * D, rph, rpw, Qx, Kx, Vt, nwb, d.nheads, S, Lkp, DK, D, HD, 1.0f / sqrtf((float)HD)));
-    SAMPT_TRY(attn_tc(c, st, Qx, Kx, Vt, nwb * d.nheads, L, L, Lkp, DK, HD, NT, d.nheads, att, D * asp, (asp == 2 && p_proj == 3) ? D : 0));
+    SAMPT_TRY(attn_tc(c, st, Qx, Kx, Vt, nwb * d.nheads, L, L, Lkp, DK, HD, NT, d.nheads, att, D * asp, (asp == 2 && p_proj == 3) ? D : 0,
+                      f8_proj));
     // x = x + proj(attn)   (window un-partition via the row map; padding rows are dropped)
     {
       GemmEpi ep{};
       ep.out32 = x; ep.resid = x; ep.bias = projb; ep.ldc = D; ep.rowmap = is_global ? nullptr : blk_wmap;
-      SAMPT_TRY(gemm_tc(c, st, att, D * asp, wproj, D * bsp, Mrows, D, D, make_seg(p_proj, D), ep));
+      if (f8_proj) {
+        ep.acc_scale = s8proj;
+        SAMPT_TRY(gemm_tc(c, st, att, D * 2, w8proj, D * 2, Mrows, D, D, make_seg_f8(D), ep));
+      } else {
+        SAMPT_TRY(gemm_tc(c, st, att, D * asp, wproj, D * bsp, Mrows, D, D, make_seg(p_proj, D), ep));
+      }
     }
     // x = x + lin2(gelu(lin1(LN2(x))))
     SAMPT_TRY(ln_rows(c, st, x, D, live_only ? tmap_c : nullptr, n2w, n2b, 1e-6f, A, D * asp, asp == 2 ? D : 0, Mmlp, D, 1, f8_l1));

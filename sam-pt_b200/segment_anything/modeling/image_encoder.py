@@ -18,11 +18,14 @@ from sampt_b200.param_tree import build_param_tree
 # over up to three segments A_hi.B_hi + A_lo.B_hi + A_hi.B_lo into one fp32 TMEM accumulator.
 #   1 = fp16 x fp16, one pass          2 = weights hi|lo, two passes          3 = MLP three passes, qkv / proj two
 #   5 = MLP + proj three passes (attention output kept as hi|lo), qkv two     4 = three passes everywhere (~fp32 products)
-# Measured on the B200 against the FULL BASELINE clips (tests/test_gpu_full_configs.py, 50 frames of C2 / 8 of the C5 slice; bar:
-# per-frame IoU >= 0.999):  3: min IoU 0.99878 / 0.99873 (fails);  5: 0.99911 / 0.99951 (one frame of C2 within 1e-4 of the bar);
-# 4: 0.99979 / 0.99961.  With random weights the mask logits are noise-like, the 12-step box refinement amplifies a 1-pixel box
-# change into ~1e-3 IoU, so the default is 4: parity first.  5 / 3 are the faster modes (+4 % / +7 % frames/s), never the headline.
-DEFAULT_PRECISION = int(os.environ.get("SAMPT_VIT_PRECISION", "4"))
+#   6 = like 4, but the two correction segments of the qkv / proj / lin1 / lin2 GEMMs are e4m3 operands on kind::f8f6f4 at twice
+#       the fp16 rate (they are 2^-12 of the result, e4m3's 2^-5 rounding leaves 2^-17): 2 fp16-pass equivalents instead of 3
+# Measured on the B200 against the FULL BASELINE clips (tests/test_gpu_full_configs.py: 50 frames of C2, 50 of C3, 8 of the C5
+# slice; bar: per-frame IoU >= 0.999), min IoU C2 / C3 / C5s:  3: 0.99878 / - / 0.99873 (fails);  5: 0.99911 / - / 0.99951 (one
+# frame of C2 within 1e-4 of the bar);  4: 0.99979 / 0.99971 / 0.99961;  6: 0.99978 / 0.99973 / 0.99966 at +16 % frames/s over 4.
+# With random weights the mask logits are noise-like and the 12-step box refinement amplifies a 1-pixel box change into ~1e-3
+# IoU, so only 4 and 6 clear the bar with margin; 6 is the default.
+DEFAULT_PRECISION = int(os.environ.get("SAMPT_VIT_PRECISION", "6"))
 
 
 class ImageEncoderViT(nn.Module):
@@ -109,7 +112,7 @@ class ImageEncoderViT(nn.Module):
                 for n in ("attn.qkv", "attn.proj", "mlp.lin1", "mlp.lin2"):
                     ctx.set_tensor(prefix + b + n + ".w16", self._w16(sd[b + n + ".weight"], split_b))
                 if self.precision == 6:
-                    for n in ("attn.qkv", "mlp.lin1", "mlp.lin2"):
+                    for n in ("attn.qkv", "attn.proj", "mlp.lin1", "mlp.lin2"):
                         w8, w8s = self._w8(sd[b + n + ".weight"])
                         ctx.set_tensor(prefix + b + n + ".w8", w8)
                         ctx.set_tensor(prefix + b + n + ".w8s", w8s)

@@ -241,8 +241,9 @@ def test_hq_encoder_interm_and_e2e(tmp_path):
     pips_sd = synth.condition_pips(synth.make_state_dict(pips_ref.pips_state_dict_shapes(), 7201))
     ckpt = synth.write_pips_checkpoint_dir(pips_sd, str(tmp_path / "pips"))
     video = synth.make_video_dict(3, 96, 128, 4)
+    taps = {}
     ref = sampt_ref.sampt_forward(pips_sd, sam_ref.RefSamPredictor(sam_sd, cfg, hq=True), video, positive_points_per_mask=4,
-                                  sam_iou_threshold=-1e9)
+                                  sam_iou_threshold=-1e9, taps=taps)
     model = factory.build_sam_pt("vit_test", sam_sd, ckpt, positive_points_per_mask=4, sam_iou_threshold=-1e9, hq=True)
     out = model(video)
     assert (out["trajectories"].cpu() - ref["trajectories"]).abs().max() < 1e-3
@@ -250,10 +251,14 @@ def test_hq_encoder_interm_and_e2e(tmp_path):
         a, b = out["logits"][0][f].cpu(), ref["logits"][0][f]
         diff = (a > 0) != (b > 0)
         # IoU >= 0.999, or -- the random-weight HQ branch yields masks of a few hundred pixels, where ONE pixel is > 0.002 IoU -- the
-        # logit-margin rule of DESIGN.md §2: at most 2 disagreeing pixels, each one undecided in the oracle itself
-        # (|logit| < 2e-3 of the frame's logit range -- the decoder parity tolerance is 3e-4 of that range per call, 13 calls chained)
+        # margin rules of DESIGN.md §2.  tol = 2e-3 of the frame's logit range (the decoder parity tolerance is 3e-4 of that range per
+        # call, 13 calls chained).  (i) final threshold: at most 2 disagreeing pixels, each undecided in the oracle (|logit| < tol);
+        # (ii) refinement box: the oracle's own box was within tol of moving by one pixel in some iteration (oracle/sampt_ref.py
+        # `_box_edge_margin`), which perturbs every later logit of the chain: then at most 1 % of the mask may disagree.
         fin = torch.isfinite(b)
         tol = 2e-3 * max(1.0, float(b[fin].abs().max()))
-        worst = float(b[diff].abs().max()) if int(diff.sum()) else 0.0
-        margin_ok = int(diff.sum()) <= 2 and worst < tol
-        assert _iou(a, b) >= 0.999 or margin_ok, (f, _iou(a, b), int(diff.sum()), int((b > 0).sum()), worst, tol)
+        nd, area = int(diff.sum()), int((b > 0).sum())
+        worst = float(b[diff].abs().max()) if nd else 0.0
+        box_margin = taps["box_margin"][(f, 0)]
+        margin_ok = (nd <= 2 and worst < tol) or (box_margin < tol and nd <= max(2, area // 100))
+        assert _iou(a, b) >= 0.999 or margin_ok, (f, _iou(a, b), nd, area, worst, tol, box_margin)
