@@ -219,6 +219,174 @@ attn_prep2_kernel(const __half* __restrict__ qkv, int ldq, const __half* __restr
   }
 }
 
+
+// ---- global-attention blocks (S = 64: 4096 tokens, 2(2S-1) = 254 table rows) ---------------------------------------------------
+// The 90 KB hi | lo table would be re-fetched by every CTA of a (chunk, head, frame) grid (10240 CTAs x 90 KB per 10-frame launch,
+// as much as the operands themselves), so this variant is PERSISTENT: one CTA per SM loads the table once and walks items
+// (frame, head, chunk of TC = 64 tokens), prefetching the q / v tiles of the next item with cp.async while the current one is
+// transposed, multiplied and written.  Same arithmetic and output as attn_prep2_kernel.
+template <int HD>
+__global__ void __launch_bounds__(256, 1)
+attn_prep2_persistent_kernel(const __half* __restrict__ qkv, int ldq, const __half* __restrict__ tab, __half* __restrict__ Qx,
+                             __half* __restrict__ Kx, __half* __restrict__ Vt, int S, int L, int Lkp, int DK, int D, int nheads, int nwb,
+                             float scale, int NRP) {
+  constexpr int QP = HD + 8, KS = HD / 16, SEG = HD / 8, TC = 64;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int TP = NRP + 8;
+  __half* sRh = reinterpret_cast<__half*>(smraw);                // [NRP][QP] Rcat hi
+  __half* sRl = sRh + (size_t)NRP * QP;                          // [NRP][QP] Rcat lo
+  __half* sqb = sRl + (size_t)NRP * QP;                          // [2][TC][QP] q (unscaled), double buffered
+  __half* svb = sqb + (size_t)2 * TC * QP;                       // [2][TC][QP] v
+  __half* sT = svb + (size_t)2 * TC * QP;                        // [TC][TP]    T = q . Rcat^T
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunk = (L + TC - 1) / TC;
+  const long long n_items = (long long)nwb * nheads * nchunk;
+
+  auto prefetch = [&](long long item, int buf) {
+    if (item < n_items) {
+      const int chunk = (int)(item % nchunk), h = (int)((item / nchunk) % nheads), wb = (int)(item / ((long long)nchunk * nheads));
+      const int t0 = chunk * TC, nt = min(TC, L - t0);
+      const __half* gq = qkv + ((size_t)wb * L + t0) * ldq + h * HD;
+      __half* sq = sqb + (size_t)buf * TC * QP;
+      __half* sv = svb + (size_t)buf * TC * QP;
+      for (int i = tid; i < TC * SEG; i += 256) {
+        const int t = i / SEG, sgm = i % SEG;
+        if (t < nt) {
+          cp_async16(sq + (size_t)t * QP + sgm * 8, gq + (size_t)t * ldq + sgm * 8);
+          cp_async16(sv + (size_t)t * QP + sgm * 8, gq + (size_t)t * ldq + 2 * D + sgm * 8);
+        } else {
+          *reinterpret_cast<uint4*>(sq + (size_t)t * QP + sgm * 8) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(sv + (size_t)t * QP + sgm * 8) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  for (int i = tid; i < 2 * NRP * QP / 8; i += 256) cp_async16(sRh + (size_t)i * 8, tab + (size_t)i * 8);
+  prefetch(blockIdx.x, 0);   // (the table rides in the first group)
+  int buf = 0;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
+    prefetch(item + gridDim.x, buf ^ 1);
+    const int chunk = (int)(item % nchunk), h = (int)((item / nchunk) % nheads), wb = (int)(item / ((long long)nchunk * nheads));
+    const int t0 = chunk * TC, nt = min(TC, L - t0);
+    const size_t bh = (size_t)wb * nheads + h;
+    const __half* gq = qkv + ((size_t)wb * L + t0) * ldq + h * HD;
+    const __half* sq = sqb + (size_t)buf * TC * QP;
+    const __half* sv = svb + (size_t)buf * TC * QP;
+    // ---- K' rows = [k | onehot(ky) | onehot(kx) | 0], global -> global (independent of the tiles in flight)
+    {
+      const int n_it = nt * SEG;
+      for (int i0 = tid; i0 < n_it; i0 += 4 * 256) {
+        uint4 kv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 256;
+          if (i < n_it) kv[u] = *reinterpret_cast<const uint4*>(gq + (size_t)(i / SEG) * ldq + D + (i % SEG) * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 256;
+          if (i < n_it) *reinterpret_cast<uint4*>(Kx + (bh * L + t0 + i / SEG) * DK + (i % SEG) * 8) = kv[u];
+        }
+      }
+      const int EXT = DK - HD;
+      for (int i = tid; i < nt * (EXT / 8); i += 256) {
+        const int t = i / (EXT / 8), e0 = (i % (EXT / 8)) * 8;
+        const int tt = t0 + t, ty = tt / S, tx = tt % S;
+        __half hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = e0 + j;
+          hv[j] = __float2half_rn((e == ty || e == S + tx) ? 1.f : 0.f);
+        }
+        *reinterpret_cast<uint4*>(Kx + (bh * L + tt) * DK + HD + e0) = *reinterpret_cast<uint4*>(hv);
+      }
+    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the prefetch of the next item has landed
+    __syncthreads();
+    // ---- V^T: a warp writes 4 rows d x 8 groups of 8 keys = 4 runs of 128 contiguous bytes; lane-rotated reads (bank spread)
+    {
+      constexpr int ngrp = TC / 8;
+      for (int w = warp; w < (HD / 4); w += 8) {
+        const int d = w * 4 + (lane >> 3);
+        const int g = lane & 7;
+        __half hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int jj = (j + (lane & 7)) & 7;
+          const int t = g * 8 + jj;
+          hv[jj] = (t < nt) ? sv[(size_t)t * QP + d] : __float2half_rn(0.f);
+        }
+        if (g < ngrp && t0 + g * 8 < Lkp) *reinterpret_cast<uint4*>(Vt + (bh * HD + d) * Lkp + t0 + g * 8) = *reinterpret_cast<uint4*>(hv);
+      }
+      if (t0 + TC >= L) {   // key padding [L, Lkp) of the last chunk
+        const int first = ((L - t0 + 7) / 8) * 8 + t0;
+        const int npad8 = max(0, Lkp - first) / 8;
+        for (int i = tid; i < HD * npad8; i += 256) {
+          const int d = i / npad8, t = first + (i % npad8) * 8;
+          *reinterpret_cast<uint4*>(Vt + (bh * HD + d) * Lkp + t) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+    // ---- T[TC x NRP] = q . Rcat^T (mma.sync m16n8k16, fp32 accumulate, Rcat = hi + lo); 4 m-tiles x 2 column halves over 8 warps
+    {
+      const int m = warp & 3, nhalf = warp >> 2, ntile = NRP / 8;
+      uint32_t af[KS][4];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) ldmatrix_x4(af[ks], sq + (size_t)(m * 16 + (lane & 15)) * QP + ks * 16 + (lane >> 4) * 8);
+      for (int n = nhalf; n < ntile; n += 2) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          uint32_t bh_[2], bl_[2];
+          const size_t off = (size_t)(n * 8 + (lane & 7)) * QP + ks * 16 + ((lane >> 3) & 1) * 8;
+          ldmatrix_x2(bh_, sRh + off);
+          ldmatrix_x2(bl_, sRl + off);
+          mma_16816(acc, af[ks], bh_);
+          mma_16816(acc, af[ks], bl_);
+        }
+        const int r0 = m * 16 + (lane >> 2), c0 = n * 8 + 2 * (lane & 3);
+        *reinterpret_cast<__half2*>(sT + (size_t)r0 * TP + c0) = __floats2half2_rn(acc[0], acc[1]);
+        *reinterpret_cast<__half2*>(sT + (size_t)(r0 + 8) * TP + c0) = __floats2half2_rn(acc[2], acc[3]);
+      }
+    }
+    __syncthreads();
+    // ---- Q' rows: [q*scale (HD) | T[t][ty - j + S-1] (S) | T[t][(2S-1) + tx - j + S-1] (S) | 0]
+    {
+      const int cpr = DK / 8;
+      for (int i = tid; i < nt * cpr; i += 256) {
+        const int t = i / cpr, c8 = (i % cpr) * 8;
+        const int tt = t0 + t, ty = tt / S, tx = tt % S;
+        __half hv[8];
+        if (c8 + 8 <= HD) {
+          const uint4 qv = *reinterpret_cast<const uint4*>(sq + (size_t)t * QP + c8);
+          const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(q2[j]);
+            reinterpret_cast<__half2*>(hv)[j] = __floats2half2_rn(f.x * scale, f.y * scale);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = c8 + j;
+            __half v;
+            if (col < HD) v = __float2half_rn(__half2float(sq[(size_t)t * QP + col]) * scale);
+            else if (col < HD + S) v = sT[(size_t)t * TP + (ty - (col - HD) + S - 1)];
+            else if (col < HD + 2 * S) v = sT[(size_t)t * TP + (2 * S - 1) + (tx - (col - HD - S) + S - 1)];
+            else v = __float2half_rn(0.f);
+            hv[j] = v;
+          }
+        }
+        *reinterpret_cast<uint4*>(Qx + (bh * L + tt) * DK + c8) = *reinterpret_cast<uint4*>(hv);
+      }
+    }
+    __syncthreads();   // sq / sv[buf] and sT are free for the prefetch / product of the iteration after next
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 static bool attn_prep2_enabled() {
   // ON unless SAMPT_ATTN_PREP2=0.  Parity-tested on hardware (encoder, C1, full C2); 436 us per windowed launch in the step against
   // 634 us for attn_prep_kernel (gpurun_out/kernel_table_prep2b.md); the first version (plain loads, uncoalesced V^T) took 748 us.
@@ -232,13 +400,16 @@ int attn_prep2(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float*
   if (!attn_prep2_enabled()) return 1;
   if (!(HD == 80 || HD == 64) || DK % 8 != 0 || DK < HD + 2 * S || (DK - HD) % 8 != 0 || Lkp % 8 != 0 || D % 8 != 0 || ldq % 8 != 0) return 1;
   const int L = S * S;
-  if (L > 256) return 1;                                        // windowed blocks only: the 64x64 global grid keeps attn_prep_kernel
-  const int TC = ((L + 15) / 16) * 16;                           // a whole 14x14 window (208 rows)
   const int NRP = ((2 * (2 * S - 1) + 7) / 8) * 8;
   const int QP = HD + 8, TP = NRP + 8;
+  const bool persistent = L > 256;                               // global blocks: table too large to re-fetch per (chunk, head, frame)
+  static const int global_on = [] { const char* e = std::getenv("SAMPT_ATTN_PREP2_GLOBAL"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+  if (persistent && !global_on) return 1;
+  const int TC = persistent ? 64 : ((L + 15) / 16) * 16;         // windowed: a whole 14x14 window (208 rows)
   const size_t sv_or_t = (size_t)TC * (size_t)std::max(QP, TP);
-  const size_t smem = ((size_t)TC * QP + sv_or_t + 2 * (size_t)NRP * QP) * sizeof(__half);
-  if (smem > 110 * 1024) return 1;                               // two CTAs per SM
+  const size_t smem = persistent ? (2 * (size_t)NRP * QP + 4 * (size_t)TC * QP + (size_t)TC * TP) * sizeof(__half)
+                                 : ((size_t)TC * QP + sv_or_t + 2 * (size_t)NRP * QP) * sizeof(__half);
+  if (smem > (persistent ? 220 : 110) * 1024) return 1;          // windowed: two CTAs per SM
   // the fp16 hi | lo table, library-owned (grows on demand)
   const size_t tab_bytes = 2 * (size_t)NRP * QP * sizeof(__half);
   auto it = c->owned.find("attn_prep2:table");
@@ -251,14 +422,26 @@ int attn_prep2(Ctx* c, cudaStream_t st, const __half* qkv, int ldq, const float*
   }
   __half* tab = reinterpret_cast<__half*>(it->second.first);
   dim3 grid(cdiv(L, TC), nheads, nwb);
+  const long long n_items = (long long)cdiv(L, TC) * nheads * nwb;
+  const int pgrid = (int)std::min<long long>(n_items, c->num_sms);
   if (HD == 80) {
     relpos_table_kernel<80><<<cdiv(NRP * QP, 256), 256, 0, st>>>(relh, relw, tab, S, NRP);
-    SAMPT_TRY(ensure_func_smem(c, "attn_prep2_kernel<80>", attn_prep2_kernel<80>, 110 * 1024));
-    attn_prep2_kernel<80><<<grid, 256, smem, st>>>(qkv, ldq, tab, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC, NRP);
+    if (persistent) {
+      SAMPT_TRY(ensure_func_smem(c, "attn_prep2_persistent_kernel<80>", attn_prep2_persistent_kernel<80>, 220 * 1024));
+      attn_prep2_persistent_kernel<80><<<pgrid, 256, smem, st>>>(qkv, ldq, tab, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, nwb, scale, NRP);
+    } else {
+      SAMPT_TRY(ensure_func_smem(c, "attn_prep2_kernel<80>", attn_prep2_kernel<80>, 110 * 1024));
+      attn_prep2_kernel<80><<<grid, 256, smem, st>>>(qkv, ldq, tab, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC, NRP);
+    }
   } else {
     relpos_table_kernel<64><<<cdiv(NRP * QP, 256), 256, 0, st>>>(relh, relw, tab, S, NRP);
-    SAMPT_TRY(ensure_func_smem(c, "attn_prep2_kernel<64>", attn_prep2_kernel<64>, 110 * 1024));
-    attn_prep2_kernel<64><<<grid, 256, smem, st>>>(qkv, ldq, tab, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC, NRP);
+    if (persistent) {
+      SAMPT_TRY(ensure_func_smem(c, "attn_prep2_persistent_kernel<64>", attn_prep2_persistent_kernel<64>, 220 * 1024));
+      attn_prep2_persistent_kernel<64><<<pgrid, 256, smem, st>>>(qkv, ldq, tab, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, nwb, scale, NRP);
+    } else {
+      SAMPT_TRY(ensure_func_smem(c, "attn_prep2_kernel<64>", attn_prep2_kernel<64>, 110 * 1024));
+      attn_prep2_kernel<64><<<grid, 256, smem, st>>>(qkv, ldq, tab, Qx, Kx, Vt, S, L, Lkp, DK, D, nheads, scale, TC, NRP);
+    }
   }
   c->launches += 2;
   SAMPT_LAUNCH_CHECK();

@@ -3,6 +3,9 @@
 // Used where the reference's numerics must be kept at float32 (PIPS MLP-Mixer: the 1e-3 px tolerance with a
 // 6-iteration feedback loop, SURVEY §7 "parity under chaos"; SAM prompt/mask decoder: 12 mask->box->mask
 // refinement iterations).  Tensor-core GEMMs (tcgen05) live in gemm_tc.cu and serve the ViT encoder.
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -163,6 +166,139 @@ sgemm_pipe_kernel(const float* __restrict__ X, int ldx, const float* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Skinny GEMM for M <= 64 rows (the N*S = 64 rows of the PIPS MLP-Mixer at 8 points: 1296 GEMMs per C2 clip on the tracker's
+// serial chain).  The pipelined kernel above gives such a shape 32-128 CTAs that each walk the whole K in 32-wide tiles with a
+// barrier per tile: 25-85 us for 0.13 GFLOP, bound by the length of that loop.  Here every CTA owns a BM x 32 output tile and
+// ONE K chunk of <= 256: the whole chunk of X and W (<= 96 KB) is requested with cp.async at once (four commit groups, consumed
+// as they land), so a CTA pays one memory round trip; K is split over a thread-block CLUSTER of KS = 1/2/4/8 CTAs whose partial
+// tiles are summed through distributed shared memory in fixed rank order (deterministic: no atomics), rank r finishing rows
+// [r*BM/KS, (r+1)*BM/KS) with bias / activation / residual.  128 CTAs for both mixer shapes (2048 x 512: 64 tiles x 2;
+// 512 x 2048: 16 tiles x 8); FMA-issue bound at ~2.4 us per CTA.
+// Shared-memory layout: k-contiguous rows with a (KC + 4)-float pitch; thread (rg, cg) owns rows rg + 16 i and columns cg + 16 j,
+// which makes the float4 operand reads of a warp conflict free.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SK_BN = 32, SK_KC = 256, SK_SUB = 64, SK_PITCH = SK_KC + 4;
+
+template <int BM>
+__global__ void __launch_bounds__(256)
+sgemm_skinny_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                    const float* residual, int ldr, float* Y, int ldy, int M, int N, int K, int kc, int act, const int* skip) {
+  if (skip != nullptr && *skip != 0) return;   // uniform over the grid: no CTA reaches a cluster barrier
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int TM = BM / 16;
+  extern __shared__ __align__(16) float smem_f[];
+  float* As = smem_f;                          // [BM][SK_PITCH]
+  float* Bs = smem_f + (size_t)BM * SK_PITCH;  // [SK_BN][SK_PITCH]
+  const int tid = threadIdx.x, cgp = tid & 15, rg = tid >> 4;
+  const int n0 = blockIdx.x * SK_BN;
+  const int KS = gridDim.y, rank = blockIdx.y;   // cluster dims (1, KS, 1): blockIdx.y is the rank inside the cluster
+  const int k_begin = rank * kc;
+  const int nsub = (min(kc, max(K - k_begin, 0)) + SK_SUB - 1) / SK_SUB;
+
+  for (int sub = 0; sub < SK_KC / SK_SUB; ++sub) {
+    if (sub < nsub) {
+      const int kb = sub * SK_SUB;
+      for (int i = tid; i < BM * (SK_SUB / 4); i += 256) {
+        const int r = i / (SK_SUB / 4), c = kb + (i % (SK_SUB / 4)) * 4;
+        const bool ok = r < M && k_begin + c < K && c < kc;
+        cp_async16(As + r * SK_PITCH + c, ok ? (X + (size_t)r * ldx + k_begin + c) : X, ok);
+      }
+      for (int i = tid; i < SK_BN * (SK_SUB / 4); i += 256) {
+        const int r = i / (SK_SUB / 4), c = kb + (i % (SK_SUB / 4)) * 4;
+        const bool ok = n0 + r < N && k_begin + c < K && c < kc;
+        cp_async16(Bs + r * SK_PITCH + c, ok ? (W + (size_t)(n0 + r) * ldw + k_begin + c) : W, ok);
+      }
+    }
+    cp_async_commit();
+  }
+
+  float acc[TM][2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) acc[i][0] = acc[i][1] = 0.f;
+
+#pragma unroll
+  for (int sub = 0; sub < SK_KC / SK_SUB; ++sub) {
+    if (sub == 0) cp_async_wait<3>();
+    else if (sub == 1) cp_async_wait<2>();
+    else if (sub == 2) cp_async_wait<1>();
+    else cp_async_wait<0>();
+    __syncthreads();
+    if (sub < nsub) {
+      const float* as = As + sub * SK_SUB;
+      const float* bs = Bs + sub * SK_SUB;
+#pragma unroll 4
+      for (int k = 0; k < SK_SUB; k += 4) {
+        float4 a[TM], b[2];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(as + (rg + 16 * i) * SK_PITCH + k);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) b[j] = *reinterpret_cast<const float4*>(bs + (cgp + 16 * j) * SK_PITCH + k);
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+            acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+            acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+            acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+          }
+      }
+    }
+  }
+  // partial tile -> this CTA's shared memory (over the dead A chunk), then the cluster sums the KS partials in rank order
+  __syncthreads();
+  float* P = smem_f;   // [BM][SK_BN + 1]
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) P[(rg + 16 * i) * (SK_BN + 1) + cgp + 16 * j] = acc[i][j];
+  cluster.sync();
+  const int rows_per = BM / KS;   // KS divides 16 <= BM
+  for (int e = tid; e < rows_per * SK_BN; e += 256) {
+    const int m = rank * rows_per + e / SK_BN, col = e % SK_BN, n = n0 + col;
+    float v = 0.f;
+    for (int s = 0; s < KS; ++s) v += cluster.map_shared_rank(P, s)[m * (SK_BN + 1) + col];
+    if (m < M && n < N) {
+      if (bias) v += bias[n];
+      if (act == 1) v = gelu_erf(v);
+      else if (act == 2) v = fmaxf(v, 0.f);
+      else if (act == 3) v = gelu_tanh(v);
+      if (residual) v += residual[(size_t)m * ldr + n];
+      Y[(size_t)m * ldy + n] = v;
+    }
+  }
+  cluster.sync();   // nobody leaves while a peer may still read its partial tile
+}
+
+template <int BM>
+static int launch_skinny(cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias, const float* residual,
+                         int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip, int num_sms) {
+  // K split: chunks of <= 256 (multiples of 64), cluster size 1/2/4/8; prefer enough CTAs to cover the SMs
+  const int n_tiles = cdiv(N, SK_BN);
+  int ks = 1;
+  while (ks < 8 && (cdiv(K, ks) > SK_KC || n_tiles * ks < num_sms / 2) && cdiv(K, 2 * ks) >= SK_SUB) ks *= 2;
+  const int kc = cdiv(cdiv(K, ks), SK_SUB) * SK_SUB;
+  if (kc > SK_KC) return 1;   // K > 2048: not a shape of this path
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_tiles, ks, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)(BM + SK_BN) * SK_PITCH * sizeof(float);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = ks; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, sgemm_skinny_kernel<BM>, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, kc, act, skip);
+  return e == cudaSuccess ? 0 : 2;
+}
+static bool skinny_enabled() {
+  static const int on = [] { const char* e = std::getenv("SAMPT_SGEMM_SKINNY"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
 template <int BM, int BN, int TM, int TN, int STAGES>
 static int launch_pipe(cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias, const float* residual,
                        int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip) {
@@ -178,6 +314,8 @@ int sgemm_init() {
   SAMPT_CUDA(cudaFuncSetAttribute(sgemm_pipe_kernel<64, 16, 4, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (64 + 16) * 36 * 4));
   SAMPT_CUDA(cudaFuncSetAttribute(sgemm_pipe_kernel<64, 64, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (64 + 64) * 36 * 4));
   SAMPT_CUDA(cudaFuncSetAttribute(sgemm_pipe_kernel<128, 64, 8, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (128 + 64) * 36 * 4));
+  SAMPT_CUDA(cudaFuncSetAttribute(sgemm_skinny_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 + SK_BN) * SK_PITCH * 4));
+  SAMPT_CUDA(cudaFuncSetAttribute(sgemm_skinny_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 + SK_BN) * SK_PITCH * 4));
   return 0;
 }
 
@@ -195,7 +333,10 @@ int sgemm_nt_skip(Ctx* c, cudaStream_t st, const float* X, int ldx, const float*
   } else if (M <= 32) {
     sgemm_smallm_kernel<32><<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   } else if (M <= 64) {
-    SAMPT_TRY((launch_pipe<64, 16, 4, 1, 4>(st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip)));
+    int rc = 1;
+    if (skinny_enabled() && K <= 8 * SK_KC) rc = launch_skinny<64>(st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip, c->num_sms);
+    SAMPT_CHECK(rc != 2, "sgemm_nt: cluster launch of the skinny kernel failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    if (rc == 1) SAMPT_TRY((launch_pipe<64, 16, 4, 1, 4>(st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip)));
   } else {
     // tile choice: the largest tile that still yields enough CTAs for 148 SMs
     const long long t128 = (long long)cdiv(M, 128) * cdiv(N, 64), t64 = (long long)cdiv(M, 64) * cdiv(N, 64);

@@ -35,8 +35,10 @@ def test_linear_f32_matches_torch():
     from sampt_b200 import native
     ctx = native.get_context("cuda")
     g = torch.Generator().manual_seed(0)
+    # (33..64 rows: the clustered split-K kernel incl. K / N tails and every cluster size; others: small-M and pipelined kernels)
     for (M, N, K, act) in [(64, 512, 520, 0), (64, 2048, 512, 1), (64, 512, 2048, 0), (5, 1040, 512, 0), (4096, 128, 256, 2),
-                           (300, 70, 36, 1)]:
+                           (300, 70, 36, 1), (33, 1040, 512, 3), (48, 70, 36, 1), (64, 4736, 64, 0), (40, 96, 2048, 2),
+                           (64, 512, 4096, 0)]:
         x = torch.randn((M, K), generator=g).cuda()
         w = (torch.randn((N, K), generator=g) / K ** 0.5).cuda()
         b = torch.randn((N,), generator=g).cuda()
