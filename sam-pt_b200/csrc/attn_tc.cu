@@ -235,10 +235,6 @@ int attn_tc(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const _
   if (attn_ws_applicable(Lk, DK, HD, NT))
     return attn_ws(c, st, Qx, Kx, Vt, BH, Lq, Lk, Lkp, DK, HD, NT, nheads, out, ld_out, split_off, out_f8);
   SAMPT_CHECK(!out_f8, "attn_tc: the fp8 output layout is written by attn_ws_kernel only");
-  if (attn_tc_v2_applicable(Lk, DK, HD))
-    return attn_tc_v2(c, st, Qx, Kx, Vt, BH, Lq, Lk, Lkp, DK, HD, nheads, out, ld_out, split_off);
-  if (attn_tc_v3_applicable(Lk, NT))
-    return attn_tc_v3(c, st, Qx, Kx, Vt, BH, Lq, Lk, Lkp, DK, HD, NT, nheads, out, ld_out, split_off);
   SAMPT_CHECK(DK % 64 == 0 && DK <= 256, "attn_tc: DK=%d must be a multiple of 64 and <= 256", DK);
   SAMPT_CHECK(HD % 16 == 0 && HD <= 128, "attn_tc: HD=%d must be a multiple of 16 and <= 128", HD);
   SAMPT_CHECK(NT % 16 == 0 && NT <= 256, "attn_tc: NT=%d must be a multiple of 16 and <= 256", NT);

@@ -1,5 +1,5 @@
-// Warp-specialised fused attention for SAM's ViT on tcgen05 (round-2 kernel; supersedes attn_tc / attn_tc_v2 / attn_tc_v3
-// for every shape it accepts).  Operands as in attn_tc.cu: Q' = [q*scale | rel-pos dot products | 0], K' = [k | one-hots | 0]
+// Warp-specialised fused attention for SAM's ViT on tcgen05 (round-2 kernel; supersedes attn_tc_kernel for every shape it
+// accepts; the two round-1 pipelining drafts attn_tc_v2 / v3 were validated this round, gained 1 % each and were removed).  Operands as in attn_tc.cu: Q' = [q*scale | rel-pos dot products | 0], K' = [k | one-hots | 0]
 // (the decomposed relative-position bias rides inside the QK^T contraction), V^T; softmax(Q'K'^T) V per (batch*window*head).
 //
 // Why the round-1 kernels sat at 6 % of the tensor peak (ncu + CUPTI, profiles/r02_attention.md): ONE softmax warpgroup, one

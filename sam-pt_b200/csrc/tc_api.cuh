@@ -55,16 +55,6 @@ bool gemm_f8c_applicable(int M, int N, int K);   // shapes the fp8-corrected seg
 int gemm_tc2(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmSeg& seg,
              const GemmEpi& ep);
 
-// pipelined variant for multi-tile attention (attn_tc_v2.cu); on unless SAMPT_ATTN_V2=0
-bool attn_tc_v2_applicable(int Lk, int DK, int HD);
-int attn_tc_v2(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp, int DK,
-               int HD, int nheads, __half* out, int ld_out, int split_off);
-
-// persistent variant for single-tile (windowed) attention (attn_tc_v3.cu); on unless SAMPT_ATTN_V3=0
-bool attn_tc_v3_applicable(int Lk, int NT);
-int attn_tc_v3(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp, int DK,
-               int HD, int NT, int nheads, __half* out, int ld_out, int split_off);
-
 // round-2 kernel: two softmax warpgroups, P in tensor memory (TS MMA), persistent (attn_ws.cu); on unless SAMPT_ATTN_WS=0
 bool attn_ws_applicable(int Lk, int DK, int HD, int NT);
 int attn_ws(Ctx* c, cudaStream_t st, const __half* Qx, const __half* Kx, const __half* Vt, int BH, int Lq, int Lk, int Lkp, int DK,
