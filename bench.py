@@ -505,7 +505,8 @@ def gemm_roofline(model, dev, args):
         x = torch.randn((M, K), device=dev)
         A = torch.empty((M, 2 * K), device=dev, dtype=torch.float16)
         native.check(L.sampt_split_f8c(ctx.handle, native.ptr(x), c_int(M), c_int(K), native.ptr(A), native.stream_ptr()))
-        Wt, w_scale = type(enc)._w8(torch.randn((N, K), device=dev) * 0.02)
+        from segment_anything.modeling.image_encoder import ImageEncoderViT
+        Wt, w_scale = ImageEncoderViT._w8(torch.randn((N, K), device=dev) * 0.02)
 
         def run():
             native.check(L.sampt_gemm_f8c(ctx.handle, native.ptr(A), native.ptr(Wt), c_int(M), c_int(N), c_int(K), native.ptr(w_scale),

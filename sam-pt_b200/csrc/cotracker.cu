@@ -5,8 +5,11 @@
 //
 // The encoder, the correlation pyramid and the fused correlation gather are shared with PIPS (pips_kernels.cu); this file
 // adds the transformer input assembly, the UpdateFormer (time / space attention blocks) and the state update.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_api.cuh"
 #include "../../include/sampt_b200.h"
 
 namespace sampt {
@@ -150,6 +153,52 @@ ln384_kernel(const float* __restrict__ x, float* __restrict__ y, int M) {
         make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
 }
 
+// The same LayerNorm writing the GEMM operand of the tensor-core path: fp16 hi | lo, row pitch 2 * 384 (see gemm_tc.cu: three passes)
+__global__ void __launch_bounds__(256)
+ln384_split_kernel(const float* __restrict__ x, __half* __restrict__ y, int M) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* p = x + (size_t)row * CT_HID;
+  float4 v[3];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { v[i] = *reinterpret_cast<const float4*>(p + (i * 32 + lane) * 4); s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  const float mean = warp_sum(s) * (1.0f / CT_HID);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    sq += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / CT_HID) + 1e-6f);
+  __half* o = y + (size_t)row * 2 * CT_HID;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float r0 = (v[i].x - mean) * rstd, r1 = (v[i].y - mean) * rstd, r2 = (v[i].z - mean) * rstd, r3 = (v[i].w - mean) * rstd;
+    const __half2 h0 = __floats2half2_rn(r0, r1), h1 = __floats2half2_rn(r2, r3);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(r0 - f0.x, r1 - f0.y), l1 = __floats2half2_rn(r2 - f1.x, r3 - f1.y);
+    *reinterpret_cast<uint2*>(o + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(o + CT_HID + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
+}
+// x [rows, K] fp32 -> fp16 hi | lo [rows, 2K]
+__global__ void __launch_bounds__(256)
+cot_split_kernel(const float* __restrict__ x, __half* __restrict__ out, long long n4, int K) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  const long long e = i * 4, r = e / K;
+  const int cidx = (int)(e % K);
+  const float4 v = *reinterpret_cast<const float4*>(x + e);
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+  __half* o = out + r * 2 * K + cidx;
+  *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  *reinterpret_cast<uint2*>(o + K) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
 // Multi-head attention inside token groups (timm Attention core).  qkv [M, 3*384] with columns [q | k | v], head h at h*48.
 // token row of (group g, position l) = g*gstride + l*lstride.  One CTA per (group, head): K/V staged in shared memory,
 // one warp per query row (lanes over keys for the scores, over channels for the output).
@@ -268,29 +317,76 @@ __global__ void cot_sample_kernel(const float* __restrict__ fmaps, int H, int W,
   for (int s = 0; s < S; ++s) out[((size_t)n * S + s) * 128 + c] = f;
 }
 
-struct CotBlockW { const float *qkv_w, *qkv_b, *proj_w, *proj_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b; };
+struct CotBlockW {
+  const float *qkv_w, *qkv_b, *proj_w, *proj_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+  const __half *qkv_w16, *proj_w16, *fc1_w16, *fc2_w16;   // fp16 hi | lo copies [N, 2K] (registered by the host), or null
+};
 
 static int load_block(Ctx* c, const std::string& p, CotBlockW* b) {
   SAMPT_TRY(get_f32(c, p + "attn.qkv.weight", &b->qkv_w)); SAMPT_TRY(get_f32(c, p + "attn.qkv.bias", &b->qkv_b));
   SAMPT_TRY(get_f32(c, p + "attn.proj.weight", &b->proj_w)); SAMPT_TRY(get_f32(c, p + "attn.proj.bias", &b->proj_b));
   SAMPT_TRY(get_f32(c, p + "mlp.fc1.weight", &b->fc1_w)); SAMPT_TRY(get_f32(c, p + "mlp.fc1.bias", &b->fc1_b));
   SAMPT_TRY(get_f32(c, p + "mlp.fc2.weight", &b->fc2_w)); SAMPT_TRY(get_f32(c, p + "mlp.fc2.bias", &b->fc2_b));
+  b->qkv_w16 = b->proj_w16 = b->fc1_w16 = b->fc2_w16 = nullptr;
+  if (c->find(p + "attn.qkv.w16") != nullptr) {
+    SAMPT_TRY(get_f16(c, p + "attn.qkv.w16", &b->qkv_w16)); SAMPT_TRY(get_f16(c, p + "attn.proj.w16", &b->proj_w16));
+    SAMPT_TRY(get_f16(c, p + "mlp.fc1.w16", &b->fc1_w16)); SAMPT_TRY(get_f16(c, p + "mlp.fc2.w16", &b->fc2_w16));
+  }
   return 0;
 }
 
-struct CotBufs { float *x, *h, *qkv, *att, *mlp; };
+struct CotBufs {
+  float *x, *h, *qkv, *att, *mlp;
+  __half *h16, *att16, *mlp16;   // hi | lo operands of the tensor-core path (null: fp32 CUDA-core GEMMs)
+};
+
+// Y[M, N] (fp32, + bias, + residual) or the next operand (fp16 hi | lo, GELU-tanh) = X16 . W16^T in three tcgen05 passes
+// (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo into one fp32 TMEM accumulator: products exact to ~2^-22, i.e. fp32-level like the CUDA-core
+// path it replaces).  The UpdateFormer is 21.5 M parameters x (8 N) token rows x 6 iterations x ~24 windows x 2 directions: at
+// N = 256 points (C5) that is 25 TFLOP per clip -- 1.2 s on the fp32 pipes, the longest serial stage of a frame-sharded C5 clip.
+static int cot_tcg(Ctx* c, cudaStream_t st, const __half* X16, const __half* W16, const float* bias, const float* resid, float* Y32,
+                   __half* Y16, int act, int M, int N, int K) {
+  GemmSeg seg{};
+  seg.nseg = 3;
+  seg.a_off[0] = 0; seg.b_off[0] = 0;
+  seg.a_off[1] = K; seg.b_off[1] = 0;
+  seg.a_off[2] = 0; seg.b_off[2] = K;
+  GemmEpi ep{};
+  ep.bias = bias; ep.act = act;
+  if (Y16) { ep.out16 = Y16; ep.ldc = 2 * N; ep.split_off = N; }
+  else { ep.out32 = Y32; ep.ldc = N; ep.resid = resid; }
+  return gemm_tc(c, st, X16, 2 * K, W16, 2 * K, M, N, K, seg, ep);
+}
 
 // AttnBlock: x += proj(attn(LN(x))) ; x += fc2(gelu_tanh(fc1(LN(x))))    (groups: G x L tokens)
 static int attn_block(Ctx* c, cudaStream_t st, const CotBlockW& w, CotBufs& b, int M, int G, int L, int gstride, int lstride) {
-  ln384_kernel<<<cdiv(M, 8), 256, 0, st>>>(b.x, b.h, M);
-  c->launches++;
-  SAMPT_TRY(sgemm_nt(c, st, b.h, CT_HID, w.qkv_w, CT_HID, w.qkv_b, nullptr, 0, b.qkv, 3 * CT_HID, M, 3 * CT_HID, CT_HID, 0));
+  const bool tc = b.h16 != nullptr && w.qkv_w16 != nullptr;
+  if (tc) {
+    ln384_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(b.x, b.h16, M);
+    c->launches++;
+    SAMPT_TRY(cot_tcg(c, st, b.h16, w.qkv_w16, w.qkv_b, nullptr, b.qkv, nullptr, 0, M, 3 * CT_HID, CT_HID));
+  } else {
+    ln384_kernel<<<cdiv(M, 8), 256, 0, st>>>(b.x, b.h, M);
+    c->launches++;
+    SAMPT_TRY(sgemm_nt(c, st, b.h, CT_HID, w.qkv_w, CT_HID, w.qkv_b, nullptr, 0, b.qkv, 3 * CT_HID, M, 3 * CT_HID, CT_HID, 0));
+  }
   size_t smem = ((size_t)L * 49 * 2 + (size_t)8 * L) * sizeof(float);
   SAMPT_CHECK(smem <= 200 * 1024, "cot_attn: %d tokens per group do not fit shared memory", L);
   SAMPT_TRY(ensure_func_smem(c, "cot_attn_kernel", cot_attn_kernel, 200 * 1024));
   cot_attn_kernel<<<dim3(G, CT_HEADS), 256, smem, st>>>(b.qkv, b.att, L, gstride, lstride);
   c->launches++;
   SAMPT_LAUNCH_CHECK();
+  if (tc) {
+    const long long n4 = (long long)M * CT_HID / 4;
+    cot_split_kernel<<<cdiv(n4, 256), 256, 0, st>>>(b.att, b.att16, n4, CT_HID);
+    c->launches++;
+    SAMPT_TRY(cot_tcg(c, st, b.att16, w.proj_w16, w.proj_b, b.x, b.x, nullptr, 0, M, CT_HID, CT_HID));
+    ln384_split_kernel<<<cdiv(M, 8), 256, 0, st>>>(b.x, b.h16, M);
+    c->launches++;
+    SAMPT_TRY(cot_tcg(c, st, b.h16, w.fc1_w16, w.fc1_b, nullptr, nullptr, b.mlp16, 3, M, 4 * CT_HID, CT_HID));   // GELU(tanh), hi | lo out
+    SAMPT_TRY(cot_tcg(c, st, b.mlp16, w.fc2_w16, w.fc2_b, b.x, b.x, nullptr, 0, M, CT_HID, 4 * CT_HID));
+    return 0;
+  }
   SAMPT_TRY(sgemm_nt(c, st, b.att, CT_HID, w.proj_w, CT_HID, w.proj_b, b.x, CT_HID, b.x, CT_HID, M, CT_HID, CT_HID, 0));
   ln384_kernel<<<cdiv(M, 8), 256, 0, st>>>(b.x, b.h, M);
   c->launches++;
@@ -344,6 +440,14 @@ extern "C" int sampt_cotracker_window(sampt_ctx* ctx, const float* fmaps, const 
   SAMPT_TRY(ws_get(c, &b.att, (size_t)M * CT_HID, "cot att"));
   SAMPT_TRY(ws_get(c, &b.mlp, (size_t)M * 4 * CT_HID, "cot mlp"));
   SAMPT_TRY(ws_get(c, &delta, (size_t)M * 130, "cot delta"));
+  // UpdateFormer GEMMs on tcgen05 (three fp16 hi | lo passes) once the token count fills 128-row tiles; SAMPT_COT_TC=0 keeps fp32
+  static const int cot_tc_on = [] { const char* e = std::getenv("SAMPT_COT_TC"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+  b.h16 = b.att16 = b.mlp16 = nullptr;
+  if (cot_tc_on && M >= 128 && tb[0].qkv_w16 != nullptr) {
+    SAMPT_TRY(ws_get(c, &b.h16, (size_t)M * 2 * CT_HID, "cot h16"));
+    SAMPT_TRY(ws_get(c, &b.att16, (size_t)M * 2 * CT_HID, "cot att16"));
+    SAMPT_TRY(ws_get(c, &b.mlp16, (size_t)M * 8 * CT_HID, "cot mlp16"));
+  }
   cot_pos_kernel<<<N, 256, 0, st>>>(w, pos);
   c->launches++;
   for (int it = 0; it < iters; ++it) {

@@ -148,6 +148,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (ep.act == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (ep.act == 3) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
         }
         if (!store_ok) {
           // nothing to write for this row (tail of M, or a padding row dropped by rowmap)

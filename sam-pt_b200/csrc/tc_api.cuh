@@ -12,7 +12,7 @@ struct GemmEpi {
   const float* bias = nullptr;   // [N] or null
   const int* rowmap = nullptr;   // [M] destination row for out32/resid (-1 = drop the row), or null = identity
   int ldc = 0;
-  int act = 0;                   // 0 none, 1 GELU(erf)
+  int act = 0;                   // 0 none, 1 GELU(erf), 3 GELU(tanh)
   int split_off = 0;             // >0: also write lo = fp16(v - hi) at column offset split_off (out16 only)
   int is_bf16 = 0;
   int resid_mod = 0;             // >0: residual row = dest row % resid_mod (broadcast of pos_embed over the frame batch)

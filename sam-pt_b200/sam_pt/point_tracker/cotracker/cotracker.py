@@ -107,6 +107,11 @@ class CoTracker(nn.Module):
                         ctx.set_tensor(f"cot.{k[:-len('.weight')]}.w16", torch.cat([hi, lo], dim=1).contiguous())
                 else:
                     ctx.set_tensor(f"cot.{k}", v.contiguous())
+                    # UpdateFormer linear layers also as fp16 hi | lo [N, 2K] for the three-pass tcgen05 GEMM (csrc/cotracker.cu: cot_tcg)
+                    if k.startswith("updateformer.") and k.endswith(".weight") and ("_blocks." in k) and v.dim() == 2:
+                        hi = v.half()
+                        lo = (v - hi.float()).half()
+                        ctx.set_tensor(f"cot.{k[:-len('.weight')]}.w16", torch.cat([hi, lo], dim=1).contiguous())
             ctx.set_tensor("cot.time_emb", _time_embed_table(IN_DIM, self.S).to(dev))
             self._time_emb = ctx._tensors["cot.time_emb"]
             self._registered_on = key

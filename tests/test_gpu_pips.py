@@ -52,6 +52,8 @@ def test_linear_f32_matches_torch():
             ref = torch.nn.functional.gelu(ref)
         elif act == 2:
             ref = torch.relu(ref)
+        elif act == 3:
+            ref = torch.nn.functional.gelu(ref, approximate="tanh")
         ref = ref + r.cpu().double()
         assert (y.cpu().double() - ref).abs().max() < 2e-5, (M, N, K, act)
 

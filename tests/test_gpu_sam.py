@@ -241,24 +241,37 @@ def test_hq_encoder_interm_and_e2e(tmp_path):
     pips_sd = synth.condition_pips(synth.make_state_dict(pips_ref.pips_state_dict_shapes(), 7201))
     ckpt = synth.write_pips_checkpoint_dir(pips_sd, str(tmp_path / "pips"))
     video = synth.make_video_dict(3, 96, 128, 4)
-    taps = {}
+    taps, cache = {}, {}
     ref = sampt_ref.sampt_forward(pips_sd, sam_ref.RefSamPredictor(sam_sd, cfg, hq=True), video, positive_points_per_mask=4,
-                                  sam_iou_threshold=-1e9, taps=taps)
+                                  sam_iou_threshold=-1e9, taps=taps, features_cache=cache)
+    # the oracle's own conditioning: the same decode on image features perturbed by 1e-5 relative (fp32 rounding level x 100).  With
+    # random weights a few border pixels sit behind a LayerNorm2d with almost no variance and move by 1e-2 (4000x the median pixel)
+    g = torch.Generator().manual_seed(1)
+
+    def pert(t):
+        if t is None:
+            return None
+        if isinstance(t, (list, tuple)):
+            return [pert(x) for x in t]
+        return t * (1 + 1e-5 * torch.randn(t.shape, generator=g))
+    cache2 = {f: {"features": pert(v["features"]), "interm": pert(v.get("interm"))} for f, v in cache.items()}
+    ref2 = sampt_ref.sampt_forward(pips_sd, sam_ref.RefSamPredictor(sam_sd, cfg, hq=True), video, positive_points_per_mask=4,
+                                   sam_iou_threshold=-1e9, features_cache=cache2)
     model = factory.build_sam_pt("vit_test", sam_sd, ckpt, positive_points_per_mask=4, sam_iou_threshold=-1e9, hq=True)
     out = model(video)
     assert (out["trajectories"].cpu() - ref["trajectories"]).abs().max() < 1e-3
+    assert torch.equal(out["visibilities"].cpu(), ref["visibilities"])
     for f in range(3):
         a, b = out["logits"][0][f].cpu(), ref["logits"][0][f]
+        sens = (ref2["logits"][0][f] - b).abs()
+        ill = sens > 100 * sens.median()                       # pixels where the ORACLE amplifies rounding noise > 100x the typical pixel
+        # everywhere else the logits agree to 2e-3 of the frame's range (3e-4 per decoder call, 13 calls chained)
+        tol = 2e-3 * max(1.0, float(b[torch.isfinite(b)].abs().max()))
+        assert float((a - b).abs()[~ill].max()) < tol, (f, float((a - b).abs()[~ill].max()), tol)
+        assert int(ill.sum()) <= 0.01 * ill.numel(), (f, int(ill.sum()))
+        # masks: IoU >= 0.999, or -- the random-weight HQ branch yields masks of ~400 pixels, where ONE pixel is 0.0025 IoU -- every
+        # disagreeing pixel is either undecided in the oracle (|logit| < tol) or ill-conditioned in the oracle itself, at most 2 of them
         diff = (a > 0) != (b > 0)
-        # IoU >= 0.999, or -- the random-weight HQ branch yields masks of a few hundred pixels, where ONE pixel is > 0.002 IoU -- the
-        # margin rules of DESIGN.md §2.  tol = 2e-3 of the frame's logit range (the decoder parity tolerance is 3e-4 of that range per
-        # call, 13 calls chained).  (i) final threshold: at most 2 disagreeing pixels, each undecided in the oracle (|logit| < tol);
-        # (ii) refinement box: the oracle's own box was within tol of moving by one pixel in some iteration (oracle/sampt_ref.py
-        # `_box_edge_margin`), which perturbs every later logit of the chain: then at most 1 % of the mask may disagree.
-        fin = torch.isfinite(b)
-        tol = 2e-3 * max(1.0, float(b[fin].abs().max()))
-        nd, area = int(diff.sum()), int((b > 0).sum())
-        worst = float(b[diff].abs().max()) if nd else 0.0
-        box_margin = taps["box_margin"][(f, 0)]
-        margin_ok = (nd <= 2 and worst < tol) or (box_margin < tol and nd <= max(2, area // 100))
-        assert _iou(a, b) >= 0.999 or margin_ok, (f, _iou(a, b), nd, area, worst, tol, box_margin)
+        nd = int(diff.sum())
+        excused = nd <= 2 and bool(((b.abs() < tol) | ill)[diff].all())
+        assert _iou(a, b) >= 0.999 or excused, (f, _iou(a, b), nd, int((b > 0).sum()))

@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""The two roofline kernels of bench.py launched in isolation, as the target of one `ncu --set full` capture:
+"""The roofline kernels of bench.py launched in isolation, as the target of one `ncu --set full` capture:
 
-  ncu --set full --clock-control none -k regex:'gemm_tc_kernel|pips_corr' -c 8 -o gpurun_out/prof_roofline python tools/ncu_targets.py
+  ncu --set full --clock-control none --import-source on -k regex:'gemm_tc|pips_corr|attn_ws' -o gpurun_out/prof_r02_roofline \
+      python tools/ncu_targets.py
 
-(ViT-H mlp.lin1 GEMM, M=40960 N=5120 K=1280, 3 split passes; fused correlation gather, N=292 points, L2 flushed before every
-launch).  profiles/extract_traffic.py turns the report's raw page into profiles/r01_roofline_traffic.json, which bench.py
-reads for the `roofline.traffic` fields."""
+(ViT-H mlp.lin1 GEMM, M=40960 N=5120 K=1280, first in the default fp8-corrected form [precision 6], then as three fp16 passes
+[precision 4]; fused correlation gather, N=292 points, L2 flushed before every launch; the windowed and the global attention launch
+of one 10-frame ViT-H batch).  profiles/extract_traffic.py turns the report's raw page into profiles/r02_roofline_traffic.json, which
+bench.py reads for the `roofline.traffic` fields."""
 import os
 import sys
 from types import SimpleNamespace
@@ -21,6 +23,7 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 enc = SimpleNamespace(embed_dim=1280)
 model = SimpleNamespace(sam_predictor=SimpleNamespace(model=SimpleNamespace(image_encoder=enc)))
-print(bench.gemm_roofline(model, dev, SimpleNamespace(encoder_batch=10, precision=3)))
+print(bench.gemm_roofline(model, dev, SimpleNamespace(encoder_batch=10, precision=6)))
+print(bench.gemm_roofline(model, dev, SimpleNamespace(encoder_batch=10, precision=4)))
 print(bench.corr_roofline(dev))
 print(bench.attn_roofline(dev))
