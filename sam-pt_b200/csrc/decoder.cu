@@ -338,60 +338,56 @@ __global__ void attn_t2i_combine_kernel(const float* __restrict__ part, float* _
   out[(size_t)t * H * DH + h * DH + d] = a / l;
 }
 
-// image tokens attend to the (few) prompt tokens: q [N, H*DH], k/v [T, H*DH].  One thread per (image token, head).
-// k/v are staged through shared memory in chunks of TCH tokens (two passes: row max, then exp / sum / weighted sum), so any number
-// of prompt tokens is supported (BASELINE configs[4]: 256 query points + other objects' positives).
+// image tokens attend to the prompt tokens: q [N, H*DH], k/v [T, H*DH].  One thread per (image token, head).
+// k/v pass through shared memory in chunks of 32 tokens (35 KB: several CTAs per SM whatever T is -- BASELINE configs[4] has 256
+// query points = 263 tokens) in a head-padded layout [t][h][DH + 1] (the 8 heads of a quarter-warp hit 8 different banks; threads of
+// the same head broadcast), ONE pass with an online softmax (running max / sum / weighted sum rescaled when the max moves).
 template <int DH>
 __global__ void __launch_bounds__(256)
 attn_kv_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, float* __restrict__ out,
-                     int N, int T, int H, int TCH, const int* skip) {
+                     int N, int T, int H, const int* skip) {
   SKIP_RETURN(skip);
-  extern __shared__ float skv[];  // k [TCH][H*DH], v [TCH][H*DH]
-  const int ld = H * DH;
+  constexpr int TCH = 32, HP = DH + 1, MAXH = 8;
+  __shared__ float sk[TCH * MAXH * HP], sv[TCH * MAXH * HP];
+  const int ld = H * DH, ldp = H * HP;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const bool live = idx < (long long)N * H;
   const int n = live ? (int)(idx / H) : 0, h = live ? (int)(idx % H) : 0;
+  const float scale = 1.0f / sqrtf((float)DH);
   float qv[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) qv[d] = q[(size_t)n * ld + h * DH + d];
-  const float scale = 1.0f / sqrtf((float)DH);
-  float mx = -INFINITY;
-  for (int t0 = 0; t0 < T; t0 += TCH) {
-    const int nt = min(TCH, T - t0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nt * ld; i += 256) skv[i] = k[(size_t)t0 * ld + i];
-    __syncthreads();
-    for (int t = 0; t < nt; ++t) {
-      const float* kp = skv + t * ld + h * DH;
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < DH; ++d) s = fmaf(qv[d], kp[d], s);
-      mx = fmaxf(mx, s * scale);
-    }
-  }
   float acc[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) acc[d] = 0.f;
-  float lsum = 0.f;
+  float mx = -INFINITY, lsum = 0.f;
   for (int t0 = 0; t0 < T; t0 += TCH) {
     const int nt = min(TCH, T - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nt * ld; i += 256) { skv[i] = k[(size_t)t0 * ld + i]; skv[TCH * ld + i] = v[(size_t)t0 * ld + i]; }
+    for (int i = threadIdx.x; i < nt * ld; i += 256) {
+      const int t = i / ld, cidx = i % ld;
+      const int o = t * ldp + (cidx / DH) * HP + (cidx % DH);
+      sk[o] = k[(size_t)t0 * ld + i];
+      sv[o] = v[(size_t)t0 * ld + i];
+    }
     __syncthreads();
     for (int t = 0; t < nt; ++t) {
-      const float* kp = skv + t * ld + h * DH;
+      const float* kp = sk + t * ldp + h * HP;
       float s = 0.f;
 #pragma unroll
       for (int d = 0; d < DH; ++d) s = fmaf(qv[d], kp[d], s);
-      float p = expf(s * scale - mx);
-      lsum += p;
-      const float* vp = skv + TCH * ld + t * ld + h * DH;
+      s *= scale;
+      const float mn = fmaxf(mx, s);
+      const float corr = expf(mx - mn), p = expf(s - mn);   // first token: exp(-inf) = 0 rescales the (zero) state
+      mx = mn;
+      lsum = fmaf(lsum, corr, p);
+      const float* vp = sv + t * ldp + h * HP;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, vp[d], acc[d]);
+      for (int d = 0; d < DH; ++d) acc[d] = fmaf(acc[d], corr, p * vp[d]);
     }
   }
   if (!live) return;
-  float inv = 1.0f / lsum;
+  const float inv = 1.0f / lsum;
 #pragma unroll
   for (int d = 0; d < DH; ++d) out[(size_t)n * ld + h * DH + d] = acc[d] * inv;
 }
@@ -889,13 +885,8 @@ static int two_way_layer(Ctx* c, cudaStream_t st, const LayerW& L, int idx, DecB
   else SAMPT_TRY(sg(c, st, b.keys, 256, L.i2t.qw, L.i2t.qb, L.peq_i2t, 128, b.iq, 128, GG, 128, 256, 0, skip));  // (keys+pe) Wq^T
   SAMPT_TRY(sg(c, st, b.qpe, 256, L.i2t.kw, L.i2t.kb, nullptr, 0, b.tk, 128, T, 128, 256, 0, skip));
   SAMPT_TRY(sg(c, st, b.queries, 256, L.i2t.vw, L.i2t.vb, nullptr, 0, b.tv, 128, T, 128, 256, 0, skip));
-  {
-    const int TCH = std::min(T, 192);   // prompt tokens staged per pass: 2 * 192 * 128 * 4 B = 192 KB of shared memory at most
-    size_t smem = (size_t)2 * TCH * 128 * sizeof(float);
-    SAMPT_TRY(ensure_func_smem(c, "attn_kv_small_kernel<16>", attn_kv_small_kernel<16>, 200 * 1024));
-    attn_kv_small_kernel<16><<<cdiv((long long)GG * 8, 256), 256, smem, st>>>(b.iq, b.tk, b.tv, b.ia, GG, T, 8, TCH, skip);
-    LAUNCH_OK();
-  }
+  attn_kv_small_kernel<16><<<cdiv((long long)GG * 8, 256), 256, 0, st>>>(b.iq, b.tk, b.tv, b.ia, GG, T, 8, skip);
+  LAUNCH_OK();
   if (L.i2t.ow16 != nullptr) {
     SAMPT_TRY(split_rows(c, st, b.ia, b.ia16, GG, 128, skip));
     SAMPT_TRY(tcg(c, st, b.ia16, L.i2t.ow16, L.i2t.ob, b.keys, b.src, 256, GG, 256, 128, skip));          // keys + attn_out

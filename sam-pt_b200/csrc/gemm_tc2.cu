@@ -28,11 +28,13 @@ using namespace tc;
 
 constexpr int P_BM = 128;          // rows per CTA (256 per pair)
 constexpr int P_BN = 256;          // tile columns (128 staged per CTA)
-constexpr int P_BK = 64, P_STAGES = 6;
+constexpr int P_BK = 64;
 constexpr int P_A_BYTES = P_BM * P_BK * 2;          // 16 KB
 constexpr int P_B_BYTES = (P_BN / 2) * P_BK * 2;    // 16 KB (this CTA's half of the B tile)
 constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// pipeline depth: 6 stages (192 KB) or 7 (224 KB, the most that fits 227 KB).  A stage is refilled every STAGES x 512 tensor cycles;
+// that period has to cover commit -> producer wake-up -> TMA issue -> L2 round trip -> full barrier -> MMA issue (~1.4 us unloaded)
+constexpr int p_smem_bytes(int stages) { return stages * P_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 constexpr int P_THREADS = 192;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;     // clears the CTA-pair peer bit of a shared::cluster address (-> even CTA)
 
@@ -94,6 +96,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
 }
 
+template <int P_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, GemmSeg seg,
                 GemmEpi ep) {
@@ -215,12 +218,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (ep.rowmap && row_ok) drow = ep.rowmap[m];
       const bool store_ok = row_ok && drow >= 0;
       const float acc_scale = ep.acc_scale ? __ldg(ep.acc_scale) : 1.0f;
-#pragma unroll 1
+      // TMEM -> registers one 32-column chunk AHEAD of the arithmetic: the load of chunk ch+1 is in flight while chunk ch is
+      // scaled / activated / stored (tcgen05.wait::ld has no group granularity, so the next load is issued right after the wait)
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P_BN);
+      uint32_t rbuf[2][32];
+      __syncwarp();
+      tmem_ld32(t_row, rbuf[0]);
+#pragma unroll
       for (int ch = 0; ch < P_BN / 32; ++ch) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P_BN + ch * 32), r);
+        uint32_t (&r)[32] = rbuf[ch & 1];
         tmem_ld_wait();
+        if (ch + 1 < P_BN / 32) tmem_ld32(t_row + (uint32_t)((ch + 1) * 32), rbuf[(ch + 1) & 1]);
         const int n0 = n_blk * P_BN + ch * 32;
         float v[32];
 #pragma unroll
@@ -320,13 +328,19 @@ bool gemm_f8c_applicable(int M, int N, int K) {
 
 int gemm_tc2(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmSeg& seg,
              const GemmEpi& ep) {
-  SAMPT_TRY(ensure_func_smem(c, "gemm_tc2_kernel", gemm_tc2_kernel, P_SMEM_BYTES));
+  static const int stages = [] { const char* e = std::getenv("SAMPT_GEMM_STAGES"); return (e != nullptr && e[0] == '6') ? 6 : 7; }();
   CUtensorMap tmA, tmB;
   SAMPT_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)lda, (uint64_t)M, (uint64_t)lda * 2, P_BK, P_BM));
   SAMPT_TRY(make_tmap_2d_f16(&tmB, B, (uint64_t)ldb, (uint64_t)N, (uint64_t)ldb * 2, P_BK, P_BN / 2));
   const int m_tiles = (M + 2 * P_BM - 1) / (2 * P_BM), n_tiles = N / P_BN;
   const int pairs = std::min(m_tiles * n_tiles, c->num_sms / 2);
-  gemm_tc2_kernel<<<2 * pairs, P_THREADS, P_SMEM_BYTES, st>>>(tmA, tmB, M, N, K, seg, ep);   // cluster dims are static (2,1,1)
+  if (stages == 7) {   // cluster dims are static (2,1,1)
+    SAMPT_TRY(ensure_func_smem(c, "gemm_tc2_kernel<7>", gemm_tc2_kernel<7>, p_smem_bytes(7)));
+    gemm_tc2_kernel<7><<<2 * pairs, P_THREADS, p_smem_bytes(7), st>>>(tmA, tmB, M, N, K, seg, ep);
+  } else {
+    SAMPT_TRY(ensure_func_smem(c, "gemm_tc2_kernel<6>", gemm_tc2_kernel<6>, p_smem_bytes(6)));
+    gemm_tc2_kernel<6><<<2 * pairs, P_THREADS, p_smem_bytes(6), st>>>(tmA, tmB, M, N, K, seg, ep);
+  }
   c->launches++;
   SAMPT_LAUNCH_CHECK();
   return 0;

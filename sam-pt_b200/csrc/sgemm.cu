@@ -195,6 +195,10 @@ sgemm_skinny_kernel(const float* __restrict__ X, int ldx, const float* __restric
   const int tid = threadIdx.x, cgp = tid & 15, rg = tid >> 4;
   const int n0 = blockIdx.x * SK_BN;
   const int KS = gridDim.y, rank = blockIdx.y;   // cluster dims (1, KS, 1): blockIdx.y is the rank inside the cluster
+  // taller problems (up to a few hundred rows: the mask decoder's token side with 256 query points) run as blockIdx.z row blocks
+  const int mz = blockIdx.z * BM;
+  X += (size_t)mz * ldx;
+  M = min(BM, M - mz);
   const int k_begin = rank * kc;
   const int nsub = (min(kc, max(K - k_begin, 0)) + SK_SUB - 1) / SK_SUB;
 
@@ -266,8 +270,8 @@ sgemm_skinny_kernel(const float* __restrict__ X, int ldx, const float* __restric
       if (act == 1) v = gelu_erf(v);
       else if (act == 2) v = fmaxf(v, 0.f);
       else if (act == 3) v = gelu_tanh(v);
-      if (residual) v += residual[(size_t)m * ldr + n];
-      Y[(size_t)m * ldy + n] = v;
+      if (residual) v += residual[(size_t)(mz + m) * ldr + n];
+      Y[(size_t)(mz + m) * ldy + n] = v;
     }
   }
   cluster.sync();   // nobody leaves while a peer may still read its partial tile
@@ -277,13 +281,13 @@ template <int BM>
 static int launch_skinny(cudaStream_t st, const float* X, int ldx, const float* W, int ldw, const float* bias, const float* residual,
                          int ldr, float* Y, int ldy, int M, int N, int K, int act, const int* skip, int num_sms) {
   // K split: chunks of <= 256 (multiples of 64), cluster size 1/2/4/8; prefer enough CTAs to cover the SMs
-  const int n_tiles = cdiv(N, SK_BN);
+  const int n_tiles = cdiv(N, SK_BN), m_blocks = cdiv(M, BM);
   int ks = 1;
-  while (ks < 8 && (cdiv(K, ks) > SK_KC || n_tiles * ks < num_sms / 2) && cdiv(K, 2 * ks) >= SK_SUB) ks *= 2;
+  while (ks < 8 && (cdiv(K, ks) > SK_KC || n_tiles * m_blocks * ks < num_sms / 2) && cdiv(K, 2 * ks) >= SK_SUB) ks *= 2;
   const int kc = cdiv(cdiv(K, ks), SK_SUB) * SK_SUB;
   if (kc > SK_KC) return 1;   // K > 2048: not a shape of this path
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(n_tiles, ks, 1);
+  cfg.gridDim = dim3(n_tiles, ks, m_blocks);
   cfg.blockDim = dim3(256, 1, 1);
   cfg.dynamicSmemBytes = (size_t)(BM + SK_BN) * SK_PITCH * sizeof(float);
   cfg.stream = st;
@@ -332,7 +336,7 @@ int sgemm_nt_skip(Ctx* c, cudaStream_t st, const float* X, int ldx, const float*
     sgemm_smallm_kernel<16><<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
   } else if (M <= 32) {
     sgemm_smallm_kernel<32><<<cdiv(N, 8), 256, 0, st>>>(X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip);
-  } else if (M <= 64) {
+  } else if (M <= 64 || (M <= 512 && skinny_enabled() && K <= 8 * SK_KC)) {
     int rc = 1;
     if (skinny_enabled() && K <= 8 * SK_KC) rc = launch_skinny<64>(st, X, ldx, W, ldw, bias, residual, ldr, Y, ldy, M, N, K, act, skip, c->num_sms);
     SAMPT_CHECK(rc != 2, "sgemm_nt: cluster launch of the skinny kernel failed (%s)", cudaGetErrorString(cudaGetLastError()));

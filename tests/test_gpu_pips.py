@@ -38,7 +38,7 @@ def test_linear_f32_matches_torch():
     # (33..64 rows: the clustered split-K kernel incl. K / N tails and every cluster size; others: small-M and pipelined kernels)
     for (M, N, K, act) in [(64, 512, 520, 0), (64, 2048, 512, 1), (64, 512, 2048, 0), (5, 1040, 512, 0), (4096, 128, 256, 2),
                            (300, 70, 36, 1), (33, 1040, 512, 3), (48, 70, 36, 1), (64, 4736, 64, 0), (40, 96, 2048, 2),
-                           (64, 512, 4096, 0)]:
+                           (64, 512, 4096, 0), (263, 2048, 256, 2), (500, 130, 384, 0), (129, 256, 2048, 1)]:
         x = torch.randn((M, K), generator=g).cuda()
         w = (torch.randn((N, K), generator=g) / K ** 0.5).cuda()
         b = torch.randn((N,), generator=g).cuda()
