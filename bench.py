@@ -392,6 +392,9 @@ def _ncu_traffic(key):
     return None if e is None else e["dram_read_bytes"] + e["dram_write_bytes"]
 
 
+ROOFLINE_WARM, ROOFLINE_REPS = 3, 10   # tools/ncu_targets.py lowers both so that one ncu --set full capture stays small
+
+
 def corr_roofline(dev, n_points=292):
     """Secondary roofline entry: the fused PIPS correlation gather (pips_corr lookup) at a large point count
     (C5-like: 256 queries + 36 support points), where it is bandwidth- rather than latency-bound.  Algorithmic bytes =
@@ -411,11 +414,11 @@ def corr_roofline(dev, n_points=292):
         native.check(native.lib().sampt_pips_corr_lookup(ctx.handle, native.ptr(lv[0]), native.ptr(lv[1]), native.ptr(lv[2]),
                                                          native.ptr(lv[3]), c_int(S), c_int(H4), c_int(W4), native.ptr(ff),
                                                          native.ptr(cc), c_int(n_points), native.ptr(out), native.stream_ptr()))
-    for _ in range(3):
+    for _ in range(ROOFLINE_WARM):
         run()
     torch.cuda.synchronize()
     times = []
-    for i in range(10):
+    for i in range(ROOFLINE_REPS):
         flush.fill_(i)  # evict the pyramid from L2 so the gather is served by HBM
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -464,11 +467,11 @@ def attn_roofline(dev, frames=10, nheads=16, hd=80):
             native.check(L_.sampt_attention_f16(ctx.handle, native.ptr(Q), native.ptr(K), native.ptr(V), c_int(BH), c_int(L), c_int(L), c_int(Lkp),
                                                 c_int(DK), c_int(hd), c_int(NT), c_int(nheads), native.ptr(o), c_int(nheads * hd), c_int(0),
                                                 native.stream_ptr()), "attention")
-        for _ in range(3):
+        for _ in range(ROOFLINE_WARM):
             run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 5
+        n = max(1, ROOFLINE_REPS // 2)
         e0.record()
         for _ in range(n):
             run()
@@ -520,11 +523,11 @@ def gemm_roofline(model, dev, args):
             native.check(L.sampt_gemm_f16(ctx.handle, native.ptr(A), c_int(K * asp), native.ptr(Wt), c_int(K * bsp), c_int(M), c_int(N),
                                           c_int(K), c_int(p), c_int(0), native.ptr(None), c_int(0), native.ptr(out), native.ptr(None),
                                           native.ptr(None), c_int(N), c_int(0), native.stream_ptr()))
-    for _ in range(3):
+    for _ in range(ROOFLINE_WARM):
         run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 10
+    n = ROOFLINE_REPS
     e0.record()
     for _ in range(n):
         run()

@@ -256,6 +256,62 @@ attn_q_small_kernel(const float* __restrict__ q, const float* __restrict__ k, co
   }
 }
 
+// Self-attention among the prompt / output tokens, any T (8 ... 263 tokens: BASELINE configs[4] carries 256 query points).
+// grid (ceil(T / 32) query tiles, H heads); the head's K and V (T x DH, padded rows) sit in shared memory; ONE WARP PER QUERY:
+// lanes stride over the keys for the scores (q from registers via shuffle-free broadcast reads), warp max / sum, probabilities to
+// shared memory, then lane d accumulates output channel d.  Replaces the block-per-(token, head) kernel above for T > 16, whose
+// 256-thread reductions of 32 accumulators cost 170 us per call at T = 263.
+template <int DH>
+__global__ void __launch_bounds__(256)
+attn_tok_self_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, float* __restrict__ out,
+                     int T, int H, const int* skip) {
+  SKIP_RETURN(skip);
+  static_assert(DH == 32, "one lane per output channel");
+  extern __shared__ float sm_ts[];
+  const int KP = DH + 1;
+  float* sk = sm_ts;                        // [T][DH + 1]
+  float* sv = sk + (size_t)T * KP;          // [T][DH + 1]
+  float* sp = sv + (size_t)T * KP;          // [8 warps][T] probabilities
+  float* sq = sp + (size_t)8 * T;           // [8 warps][DH]
+  const int h = blockIdx.y, ld = H * DH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < T * DH; i += 256) {
+    const int t = i / DH, d = i % DH;
+    sk[t * KP + d] = k[(size_t)t * ld + h * DH + d];
+    sv[t * KP + d] = v[(size_t)t * ld + h * DH + d];
+  }
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)DH);
+  float* pw = sp + (size_t)warp * T;
+  float* qw = sq + warp * DH;
+  for (int t = blockIdx.x * 32 + warp; t < min(T, blockIdx.x * 32 + 32); t += 8) {
+    qw[lane] = q[(size_t)t * ld + h * DH + lane] * scale;
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) {
+      const float* kp = sk + j * KP;
+      float sdot = 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) sdot = fmaf(qw[d], kp[d], sdot);
+      pw[j] = sdot;
+      mx = fmaxf(mx, sdot);
+    }
+    mx = warp_max(mx);
+    float lsum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float pj = expf(pw[j] - mx);
+      pw[j] = pj;
+      lsum += pj;
+    }
+    lsum = warp_sum(lsum);
+    __syncwarp();
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) acc = fmaf(pw[j], sv[j * KP + lane], acc);
+    out[(size_t)t * ld + h * DH + lane] = acc / lsum;
+    __syncwarp();   // pw / qw are rewritten by the next query of this warp
+  }
+}
+
 // tokens -> image attention, split over the keys (flash-decoding style): grid (S splits, H heads).  Each block stages its
 // slice of K/V (keys_per_split x DH, read exactly once, coalesced) in shared memory; warp w serves tokens w, w+8, ...;
 // lanes stride over the slice's keys.  Partial (max, sum, acc[DH]) per (token, head, split) -> combine kernel.
@@ -338,25 +394,30 @@ __global__ void attn_t2i_combine_kernel(const float* __restrict__ part, float* _
   out[(size_t)t * H * DH + h * DH + d] = a / l;
 }
 
-// image tokens attend to the prompt tokens: q [N, H*DH], k/v [T, H*DH].  One thread per (image token, head).
-// k/v pass through shared memory in chunks of 32 tokens (35 KB: several CTAs per SM whatever T is -- BASELINE configs[4] has 256
-// query points = 263 tokens) in a head-padded layout [t][h][DH + 1] (the 8 heads of a quarter-warp hit 8 different banks; threads of
-// the same head broadcast), ONE pass with an online softmax (running max / sum / weighted sum rescaled when the max moves).
+// image tokens attend to the prompt tokens: q [N, H*DH], k/v [T, H*DH].  One thread per (image token, head); a WARP holds 32 image
+// tokens of ONE head, so every k / v row it needs is the same for all lanes: the rows are read from shared memory as warp-uniform
+// 16-byte broadcasts (8 loads per token instead of 32 scalar ones -- the kernel was bound by shared-memory instruction issue).
+// k/v pass through shared memory in chunks of 32 tokens (32 KB: several CTAs per SM whatever T is -- BASELINE configs[4] has 256
+// query points = 263 tokens); ONE pass with an online softmax (running max / sum / weighted sum rescaled when the max moves).
 template <int DH>
 __global__ void __launch_bounds__(256)
 attn_kv_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, float* __restrict__ out,
                      int N, int T, int H, const int* skip) {
   SKIP_RETURN(skip);
-  constexpr int TCH = 32, HP = DH + 1, MAXH = 8;
-  __shared__ float sk[TCH * MAXH * HP], sv[TCH * MAXH * HP];
-  const int ld = H * DH, ldp = H * HP;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const bool live = idx < (long long)N * H;
-  const int n = live ? (int)(idx / H) : 0, h = live ? (int)(idx % H) : 0;
+  static_assert(DH % 4 == 0, "rows are read as float4");
+  constexpr int TCH = 32, MAXH = 8;
+  __shared__ __align__(16) float sk[TCH * MAXH * DH], sv[TCH * MAXH * DH];
+  const int ld = H * DH;
+  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int h = gw % H, n = (gw / H) * 32 + lane;
+  const bool live = n < N;
   const float scale = 1.0f / sqrtf((float)DH);
   float qv[DH];
 #pragma unroll
-  for (int d = 0; d < DH; ++d) qv[d] = q[(size_t)n * ld + h * DH + d];
+  for (int d = 0; d < DH; d += 4) {
+    const float4 t = live ? *reinterpret_cast<const float4*>(q + (size_t)n * ld + h * DH + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    qv[d] = t.x; qv[d + 1] = t.y; qv[d + 2] = t.z; qv[d + 3] = t.w;
+  }
   float acc[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) acc[d] = 0.f;
@@ -364,32 +425,38 @@ attn_kv_small_kernel(const float* __restrict__ q, const float* __restrict__ k, c
   for (int t0 = 0; t0 < T; t0 += TCH) {
     const int nt = min(TCH, T - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nt * ld; i += 256) {
-      const int t = i / ld, cidx = i % ld;
-      const int o = t * ldp + (cidx / DH) * HP + (cidx % DH);
-      sk[o] = k[(size_t)t0 * ld + i];
-      sv[o] = v[(size_t)t0 * ld + i];
+    for (int i = threadIdx.x; i < nt * ld / 4; i += 256) {
+      reinterpret_cast<float4*>(sk)[i] = reinterpret_cast<const float4*>(k + (size_t)t0 * ld)[i];
+      reinterpret_cast<float4*>(sv)[i] = reinterpret_cast<const float4*>(v + (size_t)t0 * ld)[i];
     }
     __syncthreads();
     for (int t = 0; t < nt; ++t) {
-      const float* kp = sk + t * ldp + h * HP;
+      const float4* kp = reinterpret_cast<const float4*>(sk + t * ld + h * DH);
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) s = fmaf(qv[d], kp[d], s);
+      for (int d = 0; d < DH / 4; ++d) {
+        const float4 kk = kp[d];
+        s = fmaf(qv[4 * d], kk.x, s); s = fmaf(qv[4 * d + 1], kk.y, s); s = fmaf(qv[4 * d + 2], kk.z, s); s = fmaf(qv[4 * d + 3], kk.w, s);
+      }
       s *= scale;
       const float mn = fmaxf(mx, s);
       const float corr = expf(mx - mn), p = expf(s - mn);   // first token: exp(-inf) = 0 rescales the (zero) state
       mx = mn;
       lsum = fmaf(lsum, corr, p);
-      const float* vp = sv + t * ldp + h * HP;
+      const float4* vp = reinterpret_cast<const float4*>(sv + t * ld + h * DH);
 #pragma unroll
-      for (int d = 0; d < DH; ++d) acc[d] = fmaf(acc[d], corr, p * vp[d]);
+      for (int d = 0; d < DH / 4; ++d) {
+        const float4 vv = vp[d];
+        acc[4 * d] = fmaf(acc[4 * d], corr, p * vv.x); acc[4 * d + 1] = fmaf(acc[4 * d + 1], corr, p * vv.y);
+        acc[4 * d + 2] = fmaf(acc[4 * d + 2], corr, p * vv.z); acc[4 * d + 3] = fmaf(acc[4 * d + 3], corr, p * vv.w);
+      }
     }
   }
   if (!live) return;
   const float inv = 1.0f / lsum;
 #pragma unroll
-  for (int d = 0; d < DH; ++d) out[(size_t)n * ld + h * DH + d] = acc[d] * inv;
+  for (int d = 0; d < DH; d += 4)
+    *reinterpret_cast<float4*>(out + (size_t)n * ld + h * DH + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -861,7 +928,14 @@ static int two_way_layer(Ctx* c, cudaStream_t st, const LayerW& L, int idx, DecB
     SAMPT_TRY(sg(c, st, b.qpe, 256, L.self_attn.kw, L.self_attn.kb, nullptr, 0, b.tk, 256, T, 256, 256, 0, skip));
   }
   SAMPT_TRY(sg(c, st, b.queries, 256, L.self_attn.vw, L.self_attn.vb, nullptr, 0, b.tv, 256, T, 256, 256, 0, skip));
-  attn_q_small_kernel<32><<<dim3(T, 8), 256, 0, st>>>(b.tq, b.tk, b.tv, b.ta, T, 8, skip);
+  if (T > 16) {
+    const size_t smem = ((size_t)2 * T * 33 + (size_t)8 * T + 8 * 32) * sizeof(float);
+    SAMPT_CHECK(smem <= 200 * 1024, "too many prompt tokens (%d) for the token self-attention", T);
+    SAMPT_TRY(ensure_func_smem(c, "attn_tok_self_kernel<32>", attn_tok_self_kernel<32>, 200 * 1024));
+    attn_tok_self_kernel<32><<<dim3(cdiv(T, 32), 8), 256, smem, st>>>(b.tq, b.tk, b.tv, b.ta, T, 8, skip);
+  } else {
+    attn_q_small_kernel<32><<<dim3(T, 8), 256, 0, st>>>(b.tq, b.tk, b.tv, b.ta, T, 8, skip);
+  }
   LAUNCH_OK();
   // layer 0 replaces the queries, later layers add (upstream skip_first_layer_pe)
   SAMPT_TRY(sg(c, st, b.ta, 256, L.self_attn.ow, L.self_attn.ob, idx == 0 ? nullptr : b.queries, 256, b.tmp, 256, T, 256, 256, 0, skip));
@@ -885,7 +959,7 @@ static int two_way_layer(Ctx* c, cudaStream_t st, const LayerW& L, int idx, DecB
   else SAMPT_TRY(sg(c, st, b.keys, 256, L.i2t.qw, L.i2t.qb, L.peq_i2t, 128, b.iq, 128, GG, 128, 256, 0, skip));  // (keys+pe) Wq^T
   SAMPT_TRY(sg(c, st, b.qpe, 256, L.i2t.kw, L.i2t.kb, nullptr, 0, b.tk, 128, T, 128, 256, 0, skip));
   SAMPT_TRY(sg(c, st, b.queries, 256, L.i2t.vw, L.i2t.vb, nullptr, 0, b.tv, 128, T, 128, 256, 0, skip));
-  attn_kv_small_kernel<16><<<cdiv((long long)GG * 8, 256), 256, 0, st>>>(b.iq, b.tk, b.tv, b.ia, GG, T, 8, skip);
+  attn_kv_small_kernel<16><<<cdiv((long long)cdiv(GG, 32) * 8, 8), 256, 0, st>>>(b.iq, b.tk, b.tv, b.ia, GG, T, 8, skip);
   LAUNCH_OK();
   if (L.i2t.ow16 != nullptr) {
     SAMPT_TRY(split_rows(c, st, b.ia, b.ia16, GG, 128, skip));

@@ -32,8 +32,10 @@ constexpr int P_BK = 64;
 constexpr int P_A_BYTES = P_BM * P_BK * 2;          // 16 KB
 constexpr int P_B_BYTES = (P_BN / 2) * P_BK * 2;    // 16 KB (this CTA's half of the B tile)
 constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
-// pipeline depth: 6 stages (192 KB) or 7 (224 KB, the most that fits 227 KB).  A stage is refilled every STAGES x 512 tensor cycles;
-// that period has to cover commit -> producer wake-up -> TMA issue -> L2 round trip -> full barrier -> MMA issue (~1.4 us unloaded)
+// pipeline depth: 6 stages (192 KB; default) or 7 (224 KB, SAMPT_GEMM_STAGES=7).  A stage is refilled every STAGES x 512 tensor
+// cycles, which has to cover commit -> producer wake-up -> TMA issue -> L2 round trip -> full barrier -> MMA issue (~1.4 us).
+// Measured on one box (gpurun_out/c10_bench*.log): 7 stages 933 / 931 ms per C2 step, 6 stages 924 ms -- the seventh stage buys
+// nothing and takes the shared memory that lets small decode kernels share the SM
 constexpr int p_smem_bytes(int stages) { return stages * P_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 constexpr int P_THREADS = 192;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;     // clears the CTA-pair peer bit of a shared::cluster address (-> even CTA)
@@ -218,17 +220,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (ep.rowmap && row_ok) drow = ep.rowmap[m];
       const bool store_ok = row_ok && drow >= 0;
       const float acc_scale = ep.acc_scale ? __ldg(ep.acc_scale) : 1.0f;
-      // TMEM -> registers one 32-column chunk AHEAD of the arithmetic: the load of chunk ch+1 is in flight while chunk ch is
-      // scaled / activated / stored (tcgen05.wait::ld has no group granularity, so the next load is issued right after the wait)
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P_BN);
-      uint32_t rbuf[2][32];
-      __syncwarp();
-      tmem_ld32(t_row, rbuf[0]);
-#pragma unroll
+      // (loading the next 32-column chunk from TMEM while this one is processed was tried: no change of the isolated GEMM time,
+      //  the epilogue is hidden behind the MMAs of the other accumulator)
+#pragma unroll 1
       for (int ch = 0; ch < P_BN / 32; ++ch) {
-        uint32_t (&r)[32] = rbuf[ch & 1];
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * P_BN + ch * 32), r);
         tmem_ld_wait();
-        if (ch + 1 < P_BN / 32) tmem_ld32(t_row + (uint32_t)((ch + 1) * 32), rbuf[(ch + 1) & 1]);
         const int n0 = n_blk * P_BN + ch * 32;
         float v[32];
 #pragma unroll
@@ -328,7 +327,7 @@ bool gemm_f8c_applicable(int M, int N, int K) {
 
 int gemm_tc2(Ctx* c, cudaStream_t st, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmSeg& seg,
              const GemmEpi& ep) {
-  static const int stages = [] { const char* e = std::getenv("SAMPT_GEMM_STAGES"); return (e != nullptr && e[0] == '6') ? 6 : 7; }();
+  static const int stages = [] { const char* e = std::getenv("SAMPT_GEMM_STAGES"); return (e != nullptr && e[0] == '7') ? 7 : 6; }();
   CUtensorMap tmA, tmB;
   SAMPT_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)lda, (uint64_t)M, (uint64_t)lda * 2, P_BK, P_BM));
   SAMPT_TRY(make_tmap_2d_f16(&tmB, B, (uint64_t)ldb, (uint64_t)N, (uint64_t)ldb * 2, P_BK, P_BN / 2));
