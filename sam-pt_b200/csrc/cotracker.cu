@@ -219,7 +219,9 @@ cot_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, int L, i
   __syncthreads();
   const float scale = 1.0f / sqrtf((float)CT_HD);
   float* pw = sp + (size_t)warp * L;
-  for (int lq = warp; lq < L; lq += 8) {
+  // blockIdx.z splits the queries of a group (space attention at 256 points has only 8 groups x 8 heads = 64 (group, head) pairs)
+  const int qchunk = (L + gridDim.z - 1) / gridDim.z, q_begin = blockIdx.z * qchunk, q_end = min(L, q_begin + qchunk);
+  for (int lq = q_begin + warp; lq < q_end; lq += 8) {
     const float* qr = qkv + (size_t)(g * gstride + lq * lstride) * (3 * CT_HID) + h * CT_HD;
     float qv[CT_HD];
 #pragma unroll
@@ -373,7 +375,9 @@ static int attn_block(Ctx* c, cudaStream_t st, const CotBlockW& w, CotBufs& b, i
   size_t smem = ((size_t)L * 49 * 2 + (size_t)8 * L) * sizeof(float);
   SAMPT_CHECK(smem <= 200 * 1024, "cot_attn: %d tokens per group do not fit shared memory", L);
   SAMPT_TRY(ensure_func_smem(c, "cot_attn_kernel", cot_attn_kernel, 200 * 1024));
-  cot_attn_kernel<<<dim3(G, CT_HEADS), 256, smem, st>>>(b.qkv, b.att, L, gstride, lstride);
+  int qsplit = 1;
+  while (qsplit < 8 && G * CT_HEADS * qsplit < 2 * c->num_sms && L / (2 * qsplit) >= 8) qsplit *= 2;
+  cot_attn_kernel<<<dim3(G, CT_HEADS, qsplit), 256, smem, st>>>(b.qkv, b.att, L, gstride, lstride);
   c->launches++;
   SAMPT_LAUNCH_CHECK();
   if (tc) {
