@@ -545,6 +545,9 @@ def gemm_roofline(model, dev, args):
             "frac": ach / pk["bf16_tflops"],                                    # ALGORITHMIC flops (2*M*N*K) / time / measured peak
             "achieved_issued": flops_exec / (ms * 1e-3) / 1e12,                 # tensor-core work issued incl. the split-precision passes
             "frac_issued": flops_exec / (ms * 1e-3) / 1e12 / pk["bf16_tflops"],
+            # the same two against the SUSTAINED peak (cuBLAS back to back under the power cap), for reference next to the burst figure
+            "peak_sustained": pk["bf16_tflops_sustained"], "frac_of_sustained": ach / pk["bf16_tflops_sustained"],
+            "frac_issued_of_sustained": flops_exec / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
             "traffic": _ncu_traffic("gemm_tc_kernel"), "algorithmic_bytes": 2.0 * (M * K * asp + N * K * bsp + M * N),
             "peak_source": pk["src"] + ", burst", "shape": [M, N, K], "passes": ("1 fp16 + 2 e4m3 (= 2 fp16-pass equivalents)" if f8c else p), "ms": ms}
 
