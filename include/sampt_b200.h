@@ -143,6 +143,8 @@ int sampt_sam_predict(sampt_ctx* ctx, const float* feat_tok, int G, const float*
                       float* iou, float* low_res, void* stream);
 /* SamPt.predict_mask (sam_pt.py:760-837) fused: [positive-only call +] full call + n_refine box/mask refinements with the
  * `mask area < 2` break evaluated on the device (no host synchronisation).  n_refine_done: device int32 [1].
+ * n_pos_first > 0: two-call form, the first call on the n_pos_first points of pos_coords / pos_labels (sam_pt.py:792-807); 0: single
+ * initial call (:783-790); < 0: two-call form with an EMPTY positive set (first call on the padding point alone).
  * graph_slot selects an independent buffer set / CUDA-graph instance (decoder slab), so chains of different frames may be
  * replayed concurrently on different streams. */
 int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, int G, const float* coords, const int* labels, int K,

@@ -1114,12 +1114,13 @@ extern "C" int sampt_sam_predict(sampt_ctx* ctx, const float* feat_tok, int G, c
 
 // SamPt.predict_mask (sam_pt.py:760-837) for negative_points_per_mask == 0 or > 0, with the iterative box refinement
 // loop run entirely on the device.  coords/labels: visible points already mapped by apply_coords (1024 frame).
-// n_pos_first: if > 0, a first call uses only the first n_pos_first (positive) points and feeds its low-res mask to the
-// second call (sam_pt.py:792-807); 0 = single initial call (:783-790).
+// n_pos_first: if > 0, a first call uses only the n_pos_first positive points and feeds its low-res mask to the second call
+// (sam_pt.py:792-807); 0 = single initial call (:783-790); < 0 = the two-call form with an EMPTY positive set (negatives are visible
+// but every positive point is occluded: the reference still runs the first predict_torch, on the padding point alone).
 // outputs: logits [H,W], iou [1], low_res [256,256], n_refine_done [1] (int, device).
 namespace sampt {
 
-struct RefineShape { int G, K, npos, nref, in_h, in_w, H, W; };
+struct RefineShape { int G, K, npos, nref, in_h, in_w, H, W; int two_pass; };
 struct RefinePtrs {
   const float* feat_tok; const float* coords; const int* labels; const float* pos_coords; const int* pos_labels;
   float* logits; float* iou; float* low_res; int* n_done; int* bbox; int* skip; float* box;
@@ -1133,13 +1134,13 @@ static int enqueue_refine_chain(Ctx* c, cudaStream_t st, DecW& w, DecBufs& b, co
   DecodeCall d{};
   d.feat_tok = p.feat_tok; d.n_masks = 1; d.tok0 = 0; d.in_h = s.in_h; d.in_w = s.in_w; d.H = s.H; d.W = s.W;
   d.logits = p.logits; d.iou = p.iou; d.low_res = p.low_res; d.skip = nullptr; d.hq_feat = p.hq_feat;
-  if (s.npos > 0) {
+  if (s.two_pass) {
     d.coords = p.pos_coords; d.labels = p.pos_labels; d.K = s.npos; d.box = nullptr; d.use_box = 0; d.mask_in = nullptr; d.bbox = nullptr;
     SAMPT_TRY(decode_once(c, st, w, b, d, s.G));
     d.mask_in = p.low_res;
   }
   d.coords = p.coords; d.labels = p.labels; d.K = s.K; d.box = nullptr; d.use_box = 0; d.bbox = p.bbox;
-  if (s.npos <= 0) d.mask_in = nullptr;
+  if (!s.two_pass) d.mask_in = nullptr;
   SAMPT_TRY(decode_once(c, st, w, b, d, s.G));
   for (int it = 0; it < s.nref; ++it) {
     refine_ctl_kernel<<<1, 1, 0, st>>>(p.bbox, p.box, p.skip, p.n_done);
@@ -1282,7 +1283,7 @@ extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, i
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DecW w;
   SAMPT_TRY(load_dec(c, &w));
-  RefineShape s{G, K, n_pos_first > 0 ? n_pos_first : 0, n_refine, in_h, in_w, H, W};
+  RefineShape s{G, K, n_pos_first > 0 ? n_pos_first : 0, n_refine, in_h, in_w, H, W, n_pos_first != 0 ? 1 : 0};
   if (c->dec_base == nullptr) {
     // eager path (no decoder slab registered): buffers from the shared workspace, kernels launched one by one.  NOT safe for
     // concurrent use from several streams (one shared workspace): the Python side forces a single decode stream here.
@@ -1321,7 +1322,7 @@ extern "C" int sampt_sam_predict_refine(sampt_ctx* ctx, const float* feat_tok, i
     }
   }
   SAMPT_CHECK(sb != nullptr, "decoder slab (%zu bytes) too small for slot %d (K=%d, %dx%d)", c->dec_bytes, graph_slot, K, H, W);
-  std::vector<int> key{G, K, s.npos, n_refine, in_h, in_w, H, W, w.n_out_tok, hq ? 1 : 0, graph_slot};
+  std::vector<int> key{G, K, s.npos, s.two_pass, n_refine, in_h, in_w, H, W, w.n_out_tok, hq ? 1 : 0, graph_slot};
   RefineGraph* g = nullptr;
   auto it = c->graph_cache.find(key);
   if (it == c->graph_cache.end()) {

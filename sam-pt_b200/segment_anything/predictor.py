@@ -177,8 +177,8 @@ class SamPredictor:
     def predict_refine(self, coords_1024: torch.Tensor, labels: torch.Tensor, n_positive_first: int, n_refine: int,
                        logits_out: torch.Tensor, slot: int = 0, positive_index=None):
         """SamPt.predict_mask (sam_pt/modeling/sam_pt.py:781-828) as ONE native call: 1 (or 2) initial predict_torch calls
-        + `n_refine` box/mask refinement iterations with the break test on the device.  coords (K,2), labels (K,) int32 on
-        the GPU; writes logits into `logits_out` (H,W) and returns (iou (1,), low_res (256,256), n_done (1,) int32)."""
+        + `n_refine` box/mask refinement iterations with the break test on the device.  n_positive_first != 0 selects the two-call
+        form (first call on the positive points only, possibly none).  coords (K,2), labels (K,) int32 on the GPU; writes logits into `logits_out` (H,W) and returns (iou (1,), low_res (256,256), n_done (1,) int32)."""
         ctx = self.model.native_context()
         tok = self._tokens()
         dev = self.device
@@ -189,7 +189,7 @@ class SamPredictor:
         ndone = torch.zeros((1,), device=dev, dtype=torch.int32)
         K = coords_1024.shape[0]
         pos_c = pos_l = None
-        if n_positive_first > 0:
+        if n_positive_first != 0:
             if positive_index is not None:   # host-known indices of the positive points: no device-side boolean indexing / sync
                 idx = torch.as_tensor(positive_index, dtype=torch.long, device=dev)
                 pos_c, pos_l = coords_1024.index_select(0, idx).contiguous(), labels.index_select(0, idx).contiguous()
@@ -198,6 +198,10 @@ class SamPredictor:
                 sel = labels == 1
                 pos_c, pos_l = coords_1024[sel].contiguous(), labels[sel].contiguous()
                 n_positive_first = int(pos_c.shape[0])
+            if n_positive_first == 0:
+                # negatives visible, every positive occluded: the reference still makes the first call, on the padding point alone
+                # (sam_pt.py:792-807 with an empty positive set) -- the native chain takes -1 for that
+                n_positive_first, pos_c, pos_l = -1, None, None
         ctx.ensure_workspace(256 << 20)
         native.check(native.lib().sampt_sam_predict_refine(
             ctx.handle, native.ptr(tok), c_int(g), native.ptr(coords_1024.contiguous()), native.ptr(labels.contiguous()), c_int(K),

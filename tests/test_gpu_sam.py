@@ -131,6 +131,35 @@ def test_predict_refine_chain_matches_oracle(decoder_setup):
     assert (g_low.cpu() - low[0, 0]).abs().max() < 5e-3 * max(1.0, low.abs().max().item())
 
 
+@pytest.mark.parametrize("n_pos", [3, 0])
+def test_predict_refine_two_call_form_matches_oracle(decoder_setup, n_pos):
+    """negative_points_per_mask > 0 (sam_pt.py:792-807): first call on the positive points only, its low-res mask feeds the second
+    call with all points; n_pos = 0 is the corner where every positive point is occluded and only negatives are visible."""
+    sd, pred, ref, g = decoder_setup
+    K = 6
+    pts = torch.rand((1, K, 2), generator=g) * torch.tensor([1000.0, 560.0])
+    labels = torch.zeros((1, K), dtype=torch.int)
+    labels[0, :n_pos] = 1
+    sel = labels[0] == 1
+    _, _, low = ref.predict_torch(pts[:, sel], labels[:, sel], None, None, False, True)
+    ml, iou, low = ref.predict_torch(pts, labels, None, low, False, True)
+    n = 0
+    for _ in range(12):
+        mm = ml[0, 0] > 0
+        if mm.sum() < 2:
+            break
+        yx = mm.nonzero()
+        box = torch.tensor([yx[:, 1].min(), yx[:, 0].min(), yx[:, 1].max(), yx[:, 0].max()], dtype=torch.float)
+        ml, iou, low = ref.predict_torch(pts, labels, box[None, None, :][:, 0], low, False, True)
+        n += 1
+    out = torch.empty((480, 854), device="cuda")
+    g_iou, g_low, g_n = pred.predict_refine(pts[0].cuda(), labels[0].cuda(), 1, 12, out, positive_index=list(range(n_pos)))
+    assert int(g_n.item()) == n
+    assert _iou(out.cpu(), ml[0, 0]) >= 0.999
+    assert (g_iou.cpu() - iou[0]).abs().max() < 1e-3
+    assert (g_low.cpu() - low[0, 0]).abs().max() < 5e-3 * max(1.0, low.abs().max().item())
+
+
 def test_sampt_c1_end_to_end(tmp_path):
     """BASELINE config C1: 2 x 240x320, ViT-B + PIPS, 4 points.  coords within 1e-3 px, per-frame IoU >= 0.999."""
     cfg = sam_ref.VIT_B
