@@ -210,6 +210,8 @@ def run_ours(args):
         kernel_table(lambda: step_resident(frames_dev, q_dev), args.kernel_table)
     # ---------------- roofline of the dominant kernel (ViT tcgen05 GEMM), measured live with CUDA events
     roof = gemm_roofline(model, dev, args)
+    if rank == 0 and world == 1:
+        roof["in_step"] = in_step_share(lambda: step_resident(frames_dev, q_dev), T, vit)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(args.config, sample_frames=args.cpu_sample_frames)
@@ -337,6 +339,40 @@ def kernel_table(step_fn, path):
         f.write("| kernel | launches | total ms | mean us | share |\n|---|---:|---:|---:|---:|\n")
         for k, c, t in rows[:60]:
             f.write(f"| `{k[:110]}` | {c} | {t / 1e3:.2f} | {t / c:.1f} | {100 * t / tot:.1f}% |\n")
+
+
+def in_step_share(step_fn, frames_per_step, vit, pattern="gemm_tc2_kernel"):
+    """Cross-check of the isolated roofline timing against the real step: one extra, untimed step under CUPTI
+    (torch.profiler); all launches of the dominant kernel are summed.  `achieved_algorithmic` uses SURVEY §8d's 5.48 TFLOP of
+    linear-layer work per ViT-H frame (what the reference computes; the padding-window skip removes ~8 % of it from the launches)."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_fn()
+            torch.cuda.synchronize()
+        tot = ker = 0.0
+        n = 0
+        for e in prof.key_averages():
+            t = getattr(e, "device_time_total", None)
+            if t is None:
+                t = getattr(e, "cuda_time_total", 0.0)
+            if t <= 0:
+                continue
+            tot += t
+            if pattern in e.key:
+                ker += t
+                n += e.count
+        out = {"kernel": pattern, "launches_per_step": int(n), "ms_per_step": ker / 1e3, "share_of_device_time": (ker / tot) if tot else None,
+               "device_ms_per_step_all_kernels": tot / 1e3, "how": "one extra untimed step under CUPTI (torch.profiler)"}
+        if vit == "vit_h" and ker > 0:
+            pk = _peaks()
+            ach = frames_per_step * 5.48 / (ker / 1e6)   # TFLOP / s
+            out.update({"achieved_algorithmic": ach, "unit": "TFLOP/s", "frac_of_sustained_peak": ach / pk["bf16_tflops_sustained"],
+                        "frac_of_burst_peak": ach / pk["bf16_tflops"]})
+        return out
+    except Exception as e:   # a profiler problem must never cost the bench line
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def stage_breakdown(model, frames_dev, q_dev):
