@@ -79,76 +79,6 @@ probe_kernel(int n_kblocks, int mode, int N, int f8, int distinct_smem, long lon
   }
 }
 
-
-// ---- the same measurement for the CTA-PAIR form the GEMM uses: tcgen05.mma.cta_group::2, M256 (128 rows per SM) x N256, each CTA
-//      holding its 128 rows of A and HALF of the B tile (128 columns); cluster (2,1,1), leader issues, both CTAs' tensor cores run
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, int f8) {
-  if (f8)
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                 "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
-                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u) : "memory");
-  else
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
-                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u), "r"(0u) : "memory");
-}
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-probe_pair_kernel(int n_kblocks, int f8, long long* cycles_out) {
-  constexpr int NSTAGE = 4, A_BYTES = 128 * 128, B_BYTES = 128 * 128;   // this CTA's half of the B tile
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + NSTAGE * (A_BYTES + B_BYTES));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool leader = cluster_ctarank() == 0;
-  for (int i = threadIdx.x; i < NSTAGE * (A_BYTES + B_BYTES) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
-  if (warp == 0) {
-    if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (warp == 1 && lane == 0 && leader) {
-    const uint32_t idesc = make_idesc_f16(256, 256, 0);
-    for (int rep = 0; rep < 2; ++rep) {
-      const long long t0 = clock64();
-      for (int kb = 0; kb < n_kblocks; ++kb) {
-        const uint32_t sa = smem_u32(smem + (kb % NSTAGE) * (A_BYTES + B_BYTES));
-        const uint64_t adesc = make_smem_desc_sw128(sa), bdesc = make_smem_desc_sw128(sa + A_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_pair(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, f8);
-      }
-      asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                   "h"((uint16_t)1) : "memory");   // arrive on the leader's barrier only
-      mbar_wait(bar, (uint32_t)rep & 1);
-      tc_fence_after();
-      const long long t1 = clock64();
-      if (rep == 1) cycles_out[blockIdx.x >> 1] = t1 - t0;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();   // the peer's tensor core works until the leader has seen the commit
-  if (warp == 0) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
 int main() {
   int dev = 0, sms = 0;
   cudaSetDevice(dev);
@@ -175,20 +105,6 @@ int main() {
                  mode == 0 ? "one (dependent)" : (mode == 1 ? "two, alternating per instr" : "two, alternating per k-block"),
                  distinct ? "4 rotating" : "1 fixed", h[sms / 2] * per, h[0] * per, h[sms - 1] * per);
         }
-  // CTA pairs (what gemm_tc2_kernel issues): M256 N256, one accumulator, operands rotating over 4 resident stages
-  const size_t smem2 = 4 * (128 * 128 + 128 * 128) + 1024 + 64;
-  cudaFuncSetAttribute(probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-  const int pairs = sms / 2;
-  for (int f8 = 0; f8 < 2; ++f8) {
-    probe_pair_kernel<<<2 * pairs, 128, smem2>>>(n_kblocks, f8, d_cyc);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("CUDA error (pair): %s\n", cudaGetErrorString(e)); return 1; }
-    cudaMemcpy(h.data(), d_cyc, sizeof(long long) * pairs, cudaMemcpyDeviceToHost);
-    std::sort(h.begin(), h.begin() + pairs);
-    const double per = 1.0 / (4.0 * n_kblocks);
-    printf("%-10s %-5s %-28s %-14s %.1f  (%.1f .. %.1f)\n", f8 ? "e4m3 K32" : "f16 K16", "256", "CTA pair (cta_group::2) M256", "4 rotating",
-           h[pairs / 2] * per, h[0] * per, h[pairs - 1] * per);
-  }
   cudaFree(d_cyc);
   return 0;
 }
